@@ -1,0 +1,134 @@
+/* pmnet_b200.h - C ABI of the B200-native PharmacoNet screening hot path.
+ *
+ * The reference (SeonghwanSeo/PharmacoNet) is pure Python and has no FFI; the interface this library replaces
+ * is the Python call chain
+ *     PharmacophoreModel._scoring(ligand, weights)      src/pmnet/pharmacophore_model.py:101-106
+ *       -> GraphMatcher(model, ligand, weights).run()   src/pmnet/scoring/graph_match.py:63-101
+ *            -> scoring_matching_pair / _self           src/pmnet/scoring/match_utils_numba.py:163-231
+ *            -> ClusterMatchTreeRoot.run / dfs_run      src/pmnet/scoring/tree.py:55-104, 219-227
+ *            -> _run_average                            src/pmnet/scoring/graph_match.py:103-109
+ * evaluated for a whole library (screening.py:46-68) in one call. The ctypes binding a maintainer of the
+ * reference would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch / C++ types. All array pointers are DEVICE pointers unless the
+ *    name says host. The caller owns every buffer; the library never allocates or frees device memory.
+ *  - all work is enqueued on the caller's CUDA stream (passed as void*, i.e. cudaStream_t); no implicit
+ *    synchronisation.
+ *  - return value 0 = OK, otherwise a PMNET_E* code; pmnet_last_error_string() gives a thread-local message.
+ *    Nothing is thrown across the ABI. Per-ligand problems are reported in out_status, not as call failures.
+ */
+#ifndef PMNET_B200_H
+#define PMNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMNET_ABI_VERSION 1
+
+/* pharmacophore types, bit positions of every type mask (graph_match.py:32-40) */
+enum {
+  PMNET_HYDROPHOBIC = 0,
+  PMNET_AROMATIC = 1,
+  PMNET_CATION = 2,
+  PMNET_ANION = 3,
+  PMNET_HBOND_DONOR = 4,
+  PMNET_HBOND_ACCEPTOR = 5,
+  PMNET_HALOGEN = 6,
+  PMNET_NUM_TYPES = 7
+};
+
+enum {
+  PMNET_OK = 0,
+  PMNET_EINVAL = 1,      /* bad argument / shape */
+  PMNET_EWORKSPACE = 2,  /* workspace too small */
+  PMNET_ELIMIT = 3,      /* model exceeds a compiled limit (nodes, clusters, shared memory) */
+  PMNET_ECUDA = 4        /* a CUDA runtime call failed */
+};
+
+/* per-ligand status written to out_status */
+enum {
+  PMNET_LIG_OK = 0,
+  PMNET_LIG_EMPTY = 1,    /* no cluster / no candidate: score 0 (graph_match.py:95-99), not an error */
+  PMNET_LIG_OVERFLOW = 2, /* per-warp scratch exhausted: score not computed; re-run with a larger scratch */
+  PMNET_LIG_UNSUPPORTED = 3 /* more conformers than PMNET_MAX_CONFORMERS */
+};
+
+#define PMNET_MAX_CONFORMERS 32   /* one warp lane per conformer */
+#define PMNET_MAX_DEPTH 20        /* graph_match.py:88 */
+#define PMNET_MIN_MATCHES 5       /* tree.py:98 */
+
+/* Pharmacophore model tables (pharmacophore_model.py:51-58, 207-365), flat.
+ * Edge tables are complete and symmetric and include the self loops (density_map.py:66-72). */
+typedef struct PmModel {
+  int32_t n_nodes;                 /* Nm <= 255 */
+  int32_t n_clusters;              /* Km <= 255 */
+  const uint8_t* node_type;        /* [Nm]     pharmacophore type index 0..6 of each model node */
+  const float* edge_mu;            /* [Nm*Nm]  ModelEdge.distance_mean as fp32 */
+  const float* edge_sigma;         /* [Nm*Nm]  ModelEdge.distance_std  as fp32 */
+  const uint8_t* cluster_mask;     /* [Km]     bit t set iff type t in ModelNodeCluster.node_types */
+  const int32_t* cluster_node_off; /* [Km+1] */
+  const uint8_t* cluster_nodes;    /* [cluster_node_off[Km]] model node indices, ascending per cluster */
+  const float* cluster_dist;       /* [Km*Km]  |centre_k - centre_l|  (graph_match.py:258-260) as fp32 */
+  const float* cluster_size_sum;   /* [Km*Km]  size_k + size_l        (graph_match.py:261) as fp32 */
+} PmModel;
+
+/* A library (or shard / chunk of one) of typed ligand graphs in CSR form (ligand.py:110-259).
+ * Clusters of a ligand are stored in matcher priority order (graph_match.py:43-60, 87).
+ * coords: node n, axis a, conformer c of ligand i at
+ *     coords[coord_off[i] + (n*3 + a)*stride_i + c],  stride_i = (n_conf[i] + 3) & ~3
+ * so that a warp (lane = conformer) reads one contiguous, 16 B-aligned row per (node, axis). */
+typedef struct PmLigandBatch {
+  int32_t n_ligands;
+  const int32_t* lig_node_off;     /* [n+1]  first node of each ligand in node_type_mask */
+  const int32_t* lig_cluster_off;  /* [n+1]  first cluster of each ligand */
+  const int32_t* cluster_node_off; /* [total clusters + 1] */
+  const uint8_t* cluster_nodes;    /* ligand-local node ids, high-priority node first (ligand.py:387-395) */
+  const uint8_t* node_type_mask;   /* [total nodes] 7-bit mask of LigandNode.types */
+  const int32_t* n_conf;           /* [n] conformers per ligand, 1..PMNET_MAX_CONFORMERS */
+  const int64_t* coord_off;        /* [n+1] in floats */
+  const float* coords;             /* fp32 node coordinates (LigandNode.positions, ligand.py:293-301) */
+} PmLigandBatch;
+
+/* Launch configuration; zero-initialise for defaults. */
+typedef struct PmScoreConfig {
+  int32_t warps_per_block;   /* default 8 */
+  int32_t blocks;            /* default: 2 x SM count */
+  int32_t scratch_rows;      /* per-warp pair-table capacity in 128 B rows; default 8192 */
+  int32_t reserved;
+} PmScoreConfig;
+
+int pmnet_abi_version(void);
+const char* pmnet_last_error_string(void);
+
+/* Bytes of device workspace pmnet_score_batch needs for this model / launch configuration. */
+size_t pmnet_score_workspace_bytes(int32_t n_model_nodes, int32_t n_model_clusters, const PmScoreConfig* cfg);
+
+/* Score every ligand of `batch` against `model` (replaces GraphMatcher.run per ligand).
+ *   model, batch : HOST structs holding DEVICE array pointers
+ *   weights      : HOST, 7 floats in PMNET_* type order (graph_match.py:32-40, 82-84)
+ *   out_scores   : [n_ligands] fp32, mean over conformers of the best leaf score (graph_match.py:103-109)
+ *   out_conf_scores : optional [n_ligands * 32] per-conformer best leaf score (lane-major), or NULL
+ *   out_status   : [n_ligands] PMNET_LIG_* code
+ *   out_stats    : optional [n_ligands * 4] uint32 {tree nodes, leaves, table rows used, pair entries}, or NULL
+ */
+int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const float* weights,
+                      float* out_scores, float* out_conf_scores, int32_t* out_status, uint32_t* out_stats,
+                      void* workspace, size_t workspace_bytes, const PmScoreConfig* cfg, void* stream);
+
+/* Keep the k best (score, ligand id) pairs of a shard, descending by score, ties by ascending id
+ * (screening.py:70 sorts the whole list; a shard only needs its top k for the final merge).
+ *   scores [n] fp32, ids = id_base + index; out_scores [k] fp32, out_ids [k] int64 (padded with -inf / -1).
+ *   workspace: pmnet_topk_workspace_bytes(n, k). */
+size_t pmnet_topk_workspace_bytes(int64_t n, int32_t k);
+int pmnet_topk(const float* scores, int64_t n, int64_t id_base, int32_t k, float* out_scores,
+               int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMNET_B200_H */
