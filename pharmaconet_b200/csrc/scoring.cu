@@ -1,0 +1,823 @@
+// scoring.cu - batched pharmacophore graph-match scoring for sm_100a (one warp per ligand, one lane per conformer).
+//
+// Replaces, for a whole library in one launch, the reference's per-ligand Python/numba path
+//   GraphMatcher.setup/run          src/pmnet/scoring/graph_match.py:85-101
+//   scoring_matching_pair/_self     src/pmnet/scoring/match_utils_numba.py:12-231
+//   ClusterMatchTree.dfs_run        src/pmnet/scoring/tree.py:55-104
+//   GraphMatcher._run_average       src/pmnet/scoring/graph_match.py:103-109
+//
+// Design:
+//  * persistent grid, warps pull ligands from a global counter (DFS cost varies by 100x between ligands);
+//  * the pharmacophore model (edge table as float4 {mu, 1/sigma, w_b/sigma, -}, cluster tables) is pinned in shared
+//    memory once per block; ligand coordinates stream from HBM as 128 B rows (lane = conformer);
+//  * phase 1 evaluates every (ligand cluster i, model cluster k) x (j, l) pair score once. Only what the tree
+//    needs is kept: a 32-bit conformer-validity word V per pair (pair score > 0) and, for pairs with V != 0, one
+//    128 B row of fp32 scores in a per-warp scratch pool;
+//  * phase 2 is the DFS with an explicit stack. Candidate sets are bit masks: a child's masks are
+//    parent_mask & alive & V, updated 32 candidates at a time (lane = candidate), the "any conformer left" tests
+//    are word != 0, per-depth control state lives in lane-indexed registers (lane d = depth d);
+//    per-conformer totals are only formed for the node being created: total' = total + self + sum of pair rows
+//    with the matched ancestors.
+// The discrete decisions (prefilter, sigma^2 < 4, fail counts, score > 0, the < 5 rule) use the same fp32
+// operations as the reference (no FMA contraction on those paths), so they agree bit for bit; the accumulated
+// scores are fp32 here (fp64 in the reference) and agree to ~1e-6 relative.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "../../include/pmnet_b200.h"
+
+namespace {
+
+constexpr int kMaxDepth = PMNET_MAX_DEPTH;      // levels
+constexpr int kSlots = kMaxDepth + 1;           // depths 0..20 (root = depth 0)
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxClusterNodes = 32;            // model nodes per model cluster handled by the match stream
+constexpr int kNmBytesPerEntry = 64;            // match-stream budget per entry (average)
+
+thread_local char g_err[256] = "";
+
+void set_err(const char* msg) {
+  int i = 0;
+  for (; msg[i] && i < 255; ++i) g_err[i] = msg[i];
+  g_err[i] = 0;
+}
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------- workspace layout (shared by host and device)
+struct WarpLayout {
+  int t_cap;        // max entries (level, model cluster) per ligand
+  int pair_cap;     // max pair entries
+  int rows;         // pair-score rows (128 B each)
+  size_t off_rows, off_v, off_prow, off_masks, off_rowbase, off_srow, off_nmoff, off_geo, off_entmc, off_entlev,
+      off_nmcnt, off_nm;
+  size_t nm_cap;
+  size_t bytes;     // per warp, multiple of 256
+};
+
+__host__ __device__ inline WarpLayout make_layout(int n_model_clusters, int scratch_rows) {
+  WarpLayout L;
+  int t = n_model_clusters * kMaxDepth;
+  if (t > 1024) t = 1024;
+  L.t_cap = (t + 31) / 32 * 32;
+  L.rows = scratch_rows;
+  L.pair_cap = scratch_rows * 4;
+  size_t o = 0;
+  L.off_rows = o;    o += (size_t)L.rows * 128;
+  L.off_v = o;       o += (size_t)L.pair_cap * 4;
+  L.off_prow = o;    o += (size_t)L.pair_cap * 4;
+  L.off_masks = o;   o += (size_t)kSlots * L.t_cap * 4;
+  L.off_rowbase = o; o += (size_t)L.t_cap * 4;
+  L.off_srow = o;    o += (size_t)L.t_cap * 4;
+  L.off_nmoff = o;   o += (size_t)L.t_cap * 4;
+  L.off_geo = o;     o += (size_t)kMaxDepth * 4 * 32 * 4;
+  L.off_entmc = o;   o += (size_t)L.t_cap;
+  L.off_entlev = o;  o += (size_t)L.t_cap;
+  L.off_nmcnt = o;   o += (size_t)L.t_cap;
+  L.off_nm = o;      L.nm_cap = (size_t)L.t_cap * kNmBytesPerEntry; o += L.nm_cap;
+  L.bytes = align_up(o, 256);
+  return L;
+}
+
+constexpr size_t kHeaderBytes = 256;
+
+// ---------------------------------------------------------------- shared-memory model image
+struct SmemModel {
+  int nm, km;
+  float4* edge;           // [nm*nm] {mu, r = 1/sigma, wr = w[type b] * r, 0}
+  float* cdist;           // [km*km]
+  float* csize;           // [km*km]
+  float* wnode;           // [nm] weight of each model node's type
+  uint16_t* cnode_off;    // [km+1]
+  uint8_t* cnodes;        // [cnode_off[km]]
+  uint8_t* ntype;         // [nm]
+  uint8_t* cmask;         // [km]
+};
+
+__host__ __device__ inline size_t smem_model_bytes(int nm, int km, int n_cluster_nodes) {
+  size_t o = 0;
+  o += (size_t)nm * nm * 16;
+  o += (size_t)km * km * 4 * 2;
+  o += (size_t)nm * 4;
+  o += align_up((size_t)(km + 1) * 2, 4);
+  o += align_up((size_t)n_cluster_nodes, 4);
+  o += align_up((size_t)nm, 4);
+  o += align_up((size_t)km, 4);
+  return align_up(o, 16);
+}
+
+struct WarpSmem {
+  float tot[kSlots][32];      // per-depth conformer totals
+  int lev_start[kMaxDepth + 1];
+  int lev_q[kMaxDepth];       // ligand cluster (global CSR index) of each level
+  int pad[3];
+};
+
+struct KernelArgs {
+  PmModel model;
+  PmLigandBatch batch;
+  float w[PMNET_NUM_TYPES];
+  float* out_scores;
+  float* out_conf;
+  int32_t* out_status;
+  uint32_t* out_stats;
+  unsigned char* workspace;
+  int scratch_rows;
+  int n_cluster_nodes;
+};
+
+__device__ __forceinline__ float ld_coord(const float* xyz, int stride, int node, int axis, int lane, bool on) {
+  return on ? __ldg(xyz + (size_t)(node * 3 + axis) * stride + lane) : 0.0f;
+}
+
+// |p1 - p2| exactly as numpy's fp32 norm (ligand.py:349-351): separate multiplies and adds, IEEE sqrt
+__device__ __forceinline__ float norm3(float dx, float dy, float dz) {
+  float s = __fmul_rn(dx, dx);
+  s = __fadd_rn(s, __fmul_rn(dy, dy));
+  s = __fadd_rn(s, __fmul_rn(dz, dz));
+  return __fsqrt_rn(s);
+}
+
+// One ligand-node pair against two matched model-node lists (match_utils_numba.py:67-86): returns the fp32
+// likelihood / (M*N) and whether this conformer fails the "half of the pairs within 2 sigma" test.
+__device__ __forceinline__ float pair_term(const SmemModel& sm, float d, const uint8_t* __restrict__ m1, int M,
+                                           const uint8_t* __restrict__ m2, int N, bool& fails) {
+  int npass = 0;
+  float lik = 0.0f;
+  for (int a = 0; a < M; ++a) {
+    const int ma = m1[a];
+    const float4* row = sm.edge + ma * sm.nm;
+    float l = 0.0f;
+    for (int b = 0; b < N; ++b) {
+      const float4 e = row[m2[b]];
+      const float s = __fmul_rn(__fsub_rn(d, e.x), e.y);
+      const float s2 = __fmul_rn(s, s);
+      l = fmaf(e.z, expf(-0.5f * s2), l);
+      npass += (s2 < 4.0f) ? 1 : 0;
+    }
+    lik = fmaf(sm.wnode[ma], l, lik);
+  }
+  const int mn = M * N;
+  fails = npass < ((mn + 1) >> 1);
+  return lik * __frcp_rn((float)mn);
+}
+
+__global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  const PmModel& gm = args.model;
+  const int NM = gm.n_nodes, KM = gm.n_clusters;
+
+  // ---- carve shared memory and load the model (once per block)
+  SmemModel sm;
+  sm.nm = NM;
+  sm.km = KM;
+  {
+    unsigned char* p = smem_raw;
+    sm.edge = (float4*)p;            p += (size_t)NM * NM * 16;
+    sm.cdist = (float*)p;            p += (size_t)KM * KM * 4;
+    sm.csize = (float*)p;            p += (size_t)KM * KM * 4;
+    sm.wnode = (float*)p;            p += (size_t)NM * 4;
+    sm.cnode_off = (uint16_t*)p;     p += align_up((size_t)(KM + 1) * 2, 4);
+    sm.cnodes = (uint8_t*)p;         p += align_up((size_t)args.n_cluster_nodes, 4);
+    sm.ntype = (uint8_t*)p;          p += align_up((size_t)NM, 4);
+    sm.cmask = (uint8_t*)p;          p += align_up((size_t)KM, 4);
+  }
+  WarpSmem* ws_all = (WarpSmem*)(smem_raw + smem_model_bytes(NM, KM, args.n_cluster_nodes));
+  WarpSmem& ws = ws_all[warp_in_block];
+
+  for (int i = threadIdx.x; i < NM * NM; i += blockDim.x) {
+    const int b = i % NM;
+    const float r = __fdiv_rn(1.0f, gm.edge_sigma[i]);
+    const float wr = __fmul_rn(args.w[gm.node_type[b]], r);
+    sm.edge[i] = make_float4(gm.edge_mu[i], r, wr, 0.0f);
+  }
+  for (int i = threadIdx.x; i < KM * KM; i += blockDim.x) {
+    sm.cdist[i] = gm.cluster_dist[i];
+    sm.csize[i] = gm.cluster_size_sum[i];
+  }
+  for (int i = threadIdx.x; i < NM; i += blockDim.x) {
+    sm.ntype[i] = gm.node_type[i];
+    sm.wnode[i] = args.w[gm.node_type[i]];
+  }
+  for (int i = threadIdx.x; i < KM; i += blockDim.x) sm.cmask[i] = gm.cluster_mask[i];
+  for (int i = threadIdx.x; i <= KM; i += blockDim.x) sm.cnode_off[i] = (uint16_t)gm.cluster_node_off[i];
+  for (int i = threadIdx.x; i < args.n_cluster_nodes; i += blockDim.x) sm.cnodes[i] = gm.cluster_nodes[i];
+  __syncthreads();
+
+  // ---- per-warp scratch
+  const WarpLayout LY = make_layout(KM, args.scratch_rows);
+  const int gwarp = blockIdx.x * warps_per_block + warp_in_block;
+  unsigned char* wbase = args.workspace + kHeaderBytes + (size_t)gwarp * LY.bytes;
+  float* const rows = (float*)(wbase + LY.off_rows);
+  uint32_t* const Vt = (uint32_t*)(wbase + LY.off_v);
+  int32_t* const prow = (int32_t*)(wbase + LY.off_prow);
+  uint32_t* const masks = (uint32_t*)(wbase + LY.off_masks);
+  int32_t* const rowbase = (int32_t*)(wbase + LY.off_rowbase);
+  int32_t* const srow = (int32_t*)(wbase + LY.off_srow);
+  uint32_t* const nmoff = (uint32_t*)(wbase + LY.off_nmoff);
+  float* const geo = (float*)(wbase + LY.off_geo);
+  uint8_t* const entmc = wbase + LY.off_entmc;
+  uint8_t* const entlev = wbase + LY.off_entlev;
+  uint8_t* const nmcnt = wbase + LY.off_nmcnt;
+  uint8_t* const nms = wbase + LY.off_nm;
+  unsigned int* const counter = (unsigned int*)args.workspace;
+
+  const PmLigandBatch& B = args.batch;
+
+  for (;;) {
+    unsigned int lig = 0;
+    if (lane == 0) lig = atomicAdd(counter, 1u);
+    lig = __shfl_sync(kFull, lig, 0);
+    if (lig >= (unsigned)B.n_ligands) break;
+
+    const int C = B.n_conf[lig];
+    float score_out = 0.0f;
+    int status = PMNET_LIG_OK;
+    uint32_t st_nodes = 0, st_leaves = 0, st_rows = 0, st_pairs = 0;
+    float best = 0.0f;
+
+    if (C < 1 || C > PMNET_MAX_CONFORMERS) {
+      status = PMNET_LIG_UNSUPPORTED;
+    } else {
+      const int stride = (C + 3) & ~3;
+      const float* xyz = B.coords + B.coord_off[lig];
+      const uint8_t* tmask = B.node_type_mask + B.lig_node_off[lig];
+      const int q0 = B.lig_cluster_off[lig], q1 = B.lig_cluster_off[lig + 1];
+      const bool on = lane < C;
+      const unsigned cmask_full = (C == 32) ? kFull : ((1u << C) - 1u);
+
+      // ================= phase 0: levels, entries, node-match streams (graph_match.py:85-92, 124-172)
+      int L = 0, T = 0;
+      uint32_t nm_used = 0;
+      bool overflow = false;
+      for (int q = q0; q < q1 && L < kMaxDepth && !overflow; ++q) {
+        const int c0 = B.cluster_node_off[q], c1 = B.cluster_node_off[q + 1];
+        unsigned m = 0;
+        for (int i = c0 + lane; i < c1; i += 32) m |= tmask[B.cluster_nodes[i]];
+        m = __reduce_or_sync(kFull, m);
+        int t_level = T;
+        for (int k0 = 0; k0 < KM; k0 += 32) {
+          const int k = k0 + lane;
+          const bool hit = (k < KM) && (sm.cmask[k] & m);
+          const unsigned bal = __ballot_sync(kFull, hit);
+          if (T + __popc(bal) > LY.t_cap) {
+            overflow = true;
+            break;
+          }
+          if (hit) {
+            const int e = T + __popc(bal & ((1u << lane) - 1u));
+            entmc[e] = (uint8_t)k;
+            entlev[e] = (uint8_t)L;
+          }
+          T += __popc(bal);
+        }
+        if (overflow) break;
+        if (T > t_level) {
+          if (lane == 0) {
+            ws.lev_start[L] = t_level;
+            ws.lev_q[L] = q;
+          }
+          // cluster centre and size per conformer (ligand.py:458-473), fp32 sequential like numpy
+          const int n = c1 - c0;
+          float cx = 0.f, cy = 0.f, cz = 0.f;
+          for (int i = c0; i < c1; ++i) {
+            const int node = B.cluster_nodes[i];
+            const float x = ld_coord(xyz, stride, node, 0, lane, on), y = ld_coord(xyz, stride, node, 1, lane, on),
+                        z = ld_coord(xyz, stride, node, 2, lane, on);
+            if (i == c0) {
+              cx = x; cy = y; cz = z;
+            } else {
+              cx = __fadd_rn(cx, x); cy = __fadd_rn(cy, y); cz = __fadd_rn(cz, z);
+            }
+          }
+          const float fn = (float)n;
+          cx = __fdiv_rn(cx, fn); cy = __fdiv_rn(cy, fn); cz = __fdiv_rn(cz, fn);
+          float sz = 0.f;
+          for (int i = c0; i < c1; ++i) {
+            const int node = B.cluster_nodes[i];
+            const float d = norm3(__fsub_rn(ld_coord(xyz, stride, node, 0, lane, on), cx),
+                                  __fsub_rn(ld_coord(xyz, stride, node, 1, lane, on), cy),
+                                  __fsub_rn(ld_coord(xyz, stride, node, 2, lane, on), cz));
+            sz = (i == c0) ? d : fmaxf(sz, d);
+          }
+          float* g = geo + (size_t)L * 128;
+          g[lane] = cx; g[32 + lane] = cy; g[64 + lane] = cz; g[96 + lane] = sz;
+          ++L;
+        }
+      }
+      __syncwarp();
+      if (!overflow && L > 0) {
+        if (lane == 0) ws.lev_start[L] = T;
+        __syncwarp();
+        // node-match streams: per entry a list of [ligand node, M, m_0..m_{M-1}] (graph_match.py:139-172)
+        for (int e0 = 0; e0 < T && !overflow; e0 += 32) {
+          const int e = e0 + lane;
+          // each lane builds the stream of one entry; sizes first, then an exclusive scan for the offsets
+          uint32_t bytes = 0;
+          int cnt = 0;
+          bool toobig = false;
+          int q = 0, k = 0;
+          if (e < T) {
+            q = ws.lev_q[entlev[e]];
+            k = entmc[e];
+            for (int i = B.cluster_node_off[q]; i < B.cluster_node_off[q + 1]; ++i) {
+              const unsigned tm = tmask[B.cluster_nodes[i]];
+              int M = 0;
+              for (int j = sm.cnode_off[k]; j < sm.cnode_off[k + 1]; ++j) M += (tm >> sm.ntype[sm.cnodes[j]]) & 1u;
+              if (M > kMaxClusterNodes) toobig = true;
+              if (M > 0) {
+                bytes += 2 + M;
+                ++cnt;
+              }
+            }
+            if (cnt > 255) toobig = true;
+          }
+          uint32_t incl = bytes;
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
+          }
+          const uint32_t total = __shfl_sync(kFull, incl, 31);
+          if (__any_sync(kFull, toobig) || nm_used + total > LY.nm_cap) {
+            overflow = true;
+            break;
+          }
+          if (e < T) {
+            uint32_t o = nm_used + incl - bytes;
+            nmoff[e] = o;
+            nmcnt[e] = (uint8_t)cnt;
+            for (int i = B.cluster_node_off[q]; i < B.cluster_node_off[q + 1]; ++i) {
+              const int node = B.cluster_nodes[i];
+              const unsigned tm = tmask[node];
+              int M = 0;
+              for (int j = sm.cnode_off[k]; j < sm.cnode_off[k + 1]; ++j) {
+                const int mn = sm.cnodes[j];
+                if ((tm >> sm.ntype[mn]) & 1u) nms[o + 2 + M++] = (uint8_t)mn;
+              }
+              if (M > 0) {
+                nms[o] = (uint8_t)node;
+                nms[o + 1] = (uint8_t)M;
+                o += 2 + M;
+              }
+            }
+          }
+          nm_used += total;
+        }
+        // pair-index base of each entry: V/prow rows of e1 cover all entries of later levels
+        if (!overflow) {
+          int run = 0;  // running pair count, computed level by level (uniform)
+          for (int l = 0; l < L; ++l) {
+            const int s = ws.lev_start[l], e_end = ws.lev_start[l + 1];
+            const int width = T - e_end;
+            for (int e = s + lane; e < e_end; e += 32) rowbase[e] = run + (e - s) * width - e_end;
+            run += (e_end - s) * width;
+          }
+          st_pairs = (uint32_t)run;
+          if (run > LY.pair_cap) overflow = true;
+        }
+        __syncwarp();
+      }
+
+      if (overflow) {
+        status = PMNET_LIG_OVERFLOW;
+      } else if (L == 0) {
+        status = PMNET_LIG_EMPTY;
+      } else {
+        // ================= phase 1: self scores and pair table (graph_match.py:222-279)
+        int nrows = 0;
+        for (int e = 0; e < T && !overflow; ++e) {
+          const int cnt = nmcnt[e];
+          int r = -1;
+          if (cnt >= 2) {
+            float sc = 0.0f;
+            uint32_t o1 = nmoff[e];
+            for (int i = 0; i < cnt; ++i) {
+              const int n1 = nms[o1], M = nms[o1 + 1];
+              const float x1 = ld_coord(xyz, stride, n1, 0, lane, on), y1 = ld_coord(xyz, stride, n1, 1, lane, on),
+                          z1 = ld_coord(xyz, stride, n1, 2, lane, on);
+              uint32_t o2 = o1 + 2 + M;
+              for (int j = i + 1; j < cnt; ++j) {
+                const int n2 = nms[o2], N = nms[o2 + 1];
+                const float d = norm3(__fsub_rn(x1, ld_coord(xyz, stride, n2, 0, lane, on)),
+                                      __fsub_rn(y1, ld_coord(xyz, stride, n2, 1, lane, on)),
+                                      __fsub_rn(z1, ld_coord(xyz, stride, n2, 2, lane, on)));
+                bool f;
+                sc += pair_term(sm, d, nms + o1 + 2, M, nms + o2 + 2, N, f);
+                o2 += 2 + N;
+              }
+              o1 += 2 + M;
+            }
+            if (nrows >= LY.rows) {
+              overflow = true;
+              break;
+            }
+            r = nrows++;
+            rows[(size_t)r * 32 + lane] = sc;
+          }
+          if (lane == 0) srow[e] = r;
+        }
+        for (int i = 0; i < L - 1 && !overflow; ++i) {
+          const float* gi = geo + (size_t)i * 128;
+          const float cix = gi[lane], ciy = gi[32 + lane], ciz = gi[64 + lane], csi = gi[96 + lane];
+          const int s1 = ws.lev_start[i], e1_end = ws.lev_start[i + 1];
+          for (int j = i + 1; j < L && !overflow; ++j) {
+            const float* gj = geo + (size_t)j * 128;
+            const float ldist = norm3(__fsub_rn(cix, gj[lane]), __fsub_rn(ciy, gj[32 + lane]), __fsub_rn(ciz, gj[64 + lane]));
+            const float lsize = __fadd_rn(csi, gj[96 + lane]);
+            const int s2 = ws.lev_start[j], e2_end = ws.lev_start[j + 1];
+            for (int e1 = s1; e1 < e1_end && !overflow; ++e1) {
+              const int k = entmc[e1];
+              const int cnt1 = nmcnt[e1];
+              const uint32_t off1 = nmoff[e1];
+              const int pb = rowbase[e1];
+              for (int e2 = s2; e2 < e2_end; ++e2) {
+                const int l = entmc[e2];
+                // cluster prefilter (graph_match.py:263-268): min_c(|d_lig - d_mod| - size_lig) > size_mod
+                const float v = __fsub_rn(fabsf(__fsub_rn(ldist, sm.cdist[k * KM + l])), lsize);
+                const bool far = !on || (v > sm.csize[k * KM + l]);
+                unsigned valid = 0;
+                int r = -1;
+                if (!__all_sync(kFull, far)) {
+                  const int cnt2 = nmcnt[e2];
+                  const int thr2 = cnt1 * cnt2;  // fail <= 0.5*cnt1*cnt2  <=>  2*fail <= cnt1*cnt2
+                  float sc = 0.0f;
+                  int nfail = 0;
+                  bool dead = false;
+                  uint32_t o1 = off1;
+                  for (int a = 0; a < cnt1 && !dead; ++a) {
+                    const int n1 = nms[o1], M = nms[o1 + 1];
+                    const float x1 = ld_coord(xyz, stride, n1, 0, lane, on), y1 = ld_coord(xyz, stride, n1, 1, lane, on),
+                                z1 = ld_coord(xyz, stride, n1, 2, lane, on);
+                    uint32_t o2 = nmoff[e2];
+                    for (int b = 0; b < cnt2; ++b) {
+                      const int n2 = nms[o2], N = nms[o2 + 1];
+                      const float d = norm3(__fsub_rn(x1, ld_coord(xyz, stride, n2, 0, lane, on)),
+                                            __fsub_rn(y1, ld_coord(xyz, stride, n2, 1, lane, on)),
+                                            __fsub_rn(z1, ld_coord(xyz, stride, n2, 2, lane, on)));
+                      bool f;
+                      sc += pair_term(sm, d, nms + o1 + 2, M, nms + o2 + 2, N, f);
+                      nfail += f ? 1 : 0;
+                      // early exit when every conformer already failed (match_utils_numba.py:191-192)
+                      if (__all_sync(kFull, !on || (2 * nfail > thr2))) {
+                        dead = true;
+                        break;
+                      }
+                      o2 += 2 + N;
+                    }
+                    o1 += 2 + M;
+                  }
+                  if (!dead) valid = __ballot_sync(kFull, on && (2 * nfail <= thr2) && (sc > 0.0f));
+                  if (valid) {
+                    if (nrows >= LY.rows) {
+                      overflow = true;
+                      break;
+                    }
+                    r = nrows++;
+                    rows[(size_t)r * 32 + lane] = sc;
+                  }
+                }
+                if (lane == 0) {
+                  Vt[pb + e2] = valid;
+                  prow[pb + e2] = r;
+                }
+              }
+            }
+          }
+        }
+        st_rows = (uint32_t)nrows;
+        __syncwarp();
+
+        if (overflow) {
+          status = PMNET_LIG_OVERFLOW;
+        } else {
+          // ================= phase 2: DFS (tree.py:55-104) with an explicit stack; lane d holds depth d's state
+          int st_cursor = 0, st_maxm = 0, st_nchild = 0, st_phase = 0, st_nmatch = 0, st_entry = -1, st_mslot = 0,
+              st_tslot = 0, st_pbase = 0;
+          unsigned st_alive = 0;
+          for (int e = lane; e < T; e += 32) masks[e] = cmask_full;
+          ws.tot[0][lane] = 0.0f;
+          if (lane == 0) {
+            st_cursor = 0;  // lev_start[0]
+            st_alive = cmask_full;
+          }
+          __syncwarp();
+          st_nodes = 1;
+          int d = 0;
+          for (;;) {
+            // node at depth d; its children live at level y = d
+            const int y = d;
+            const int phase = __shfl_sync(kFull, st_phase, d);
+            const int mslot = __shfl_sync(kFull, st_mslot, d);
+            const int tslot = __shfl_sync(kFull, st_tslot, d);
+            const uint32_t* pm = masks + (size_t)mslot * LY.t_cap;
+            bool do_return = false;
+            if (phase == 0) {
+              int cur = __shfl_sync(kFull, st_cursor, d);
+              const int end = ws.lev_start[y + 1];
+              int found = -1;
+              unsigned alive2 = 0;
+              while (cur < end) {
+                const int idx = cur + lane;
+                const unsigned mw = (idx < end) ? pm[idx] : 0u;
+                const unsigned bal = __ballot_sync(kFull, mw != 0u);
+                if (bal) {
+                  const int src = __ffs(bal) - 1;
+                  found = cur + src;
+                  alive2 = __shfl_sync(kFull, mw, src);
+                  break;
+                }
+                cur += 32;
+              }
+              if (found >= 0) {
+                // ---- matched child (y, found): ClusterMatchTree.__init__ (tree.py:33-41)
+                ++st_nodes;
+                if (lane == d) {
+                  st_cursor = found + 1;
+                  st_nchild += 1;
+                }
+                float acc = 0.0f;
+                for (int dd = 1; dd <= d; ++dd) {
+                  const int en = __shfl_sync(kFull, st_entry, dd);
+                  const int pb = __shfl_sync(kFull, st_pbase, dd);
+                  if (en >= 0) acc += rows[(size_t)prow[pb + found] * 32 + lane];
+                }
+                float t = ws.tot[tslot][lane];
+                const int sr = srow[found];
+                if (sr >= 0) t += rows[(size_t)sr * 32 + lane];
+                t += acc;
+                if (y == L - 1) {
+                  // leaf (graph_match.py:103-109)
+                  ++st_leaves;
+                  if ((alive2 >> lane) & 1u) best = fmaxf(best, t);
+                  if (lane == d) st_maxm = max(st_maxm, 1);
+                } else {
+                  const int nmatch = __shfl_sync(kFull, st_nmatch, d) + 1;
+                  const int pbc = rowbase[found];
+                  uint32_t* nm_ = masks + (size_t)(d + 1) * LY.t_cap;
+                  for (int e2 = ws.lev_start[y + 1] + lane; e2 < T; e2 += 32) nm_[e2] = pm[e2] & alive2 & Vt[pbc + e2];
+                  ws.tot[d + 1][lane] = t;
+                  if (lane == d + 1) {
+                    st_cursor = ws.lev_start[y + 1];
+                    st_maxm = 0;
+                    st_nchild = 0;
+                    st_phase = 0;
+                    st_nmatch = nmatch;
+                    st_entry = found;
+                    st_mslot = d + 1;
+                    st_tslot = d + 1;
+                    st_pbase = pbc;
+                    st_alive = alive2;
+                  }
+                  __syncwarp();
+                  d = d + 1;
+                }
+                continue;
+              }
+              // ---- no matched child left: None child iff nothing matched or too few matches so far (tree.py:98)
+              const int nchild = __shfl_sync(kFull, st_nchild, d);
+              const int nmatch = __shfl_sync(kFull, st_nmatch, d);
+              const int maxm = __shfl_sync(kFull, st_maxm, d);
+              if (nchild == 0 || nmatch + maxm < PMNET_MIN_MATCHES) {
+                ++st_nodes;
+                if (lane == d) st_phase = 1;
+                const unsigned alive = __shfl_sync(kFull, st_alive, d);
+                if (y == L - 1) {
+                  ++st_leaves;
+                  const float t = ws.tot[tslot][lane];
+                  if ((alive >> lane) & 1u) best = fmaxf(best, t);
+                  do_return = true;
+                } else {
+                  if (lane == d + 1) {
+                    st_cursor = ws.lev_start[y + 1];
+                    st_maxm = 0;
+                    st_nchild = 0;
+                    st_phase = 0;
+                    st_nmatch = nmatch;
+                    st_entry = -1;
+                    st_mslot = mslot;
+                    st_tslot = tslot;
+                    st_pbase = 0;
+                    st_alive = alive;
+                  }
+                  d = d + 1;
+                  continue;
+                }
+              } else {
+                do_return = true;
+              }
+            } else {
+              do_return = true;  // the None child returned
+            }
+            if (do_return) {
+              if (d == 0) break;
+              const int ret = __shfl_sync(kFull, st_maxm, d) + (__shfl_sync(kFull, st_entry, d) >= 0 ? 1 : 0);
+              if (lane == d - 1) st_maxm = max(st_maxm, ret);
+              d = d - 1;
+            }
+          }
+          // mean over conformers (graph_match.py:109)
+          double s = on ? (double)best : 0.0;
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+          score_out = (float)(s / (double)C);
+        }
+      }
+    }
+    if (lane == 0) {
+      args.out_scores[lig] = score_out;
+      args.out_status[lig] = status;
+      if (args.out_stats) {
+        uint32_t* o = args.out_stats + (size_t)lig * 4;
+        o[0] = st_nodes;  // tree nodes incl. the root
+        o[1] = st_leaves;
+        o[2] = st_rows;
+        o[3] = st_pairs;
+      }
+    }
+    if (args.out_conf) args.out_conf[(size_t)lig * 32 + lane] = (status == PMNET_LIG_OK) ? best : 0.0f;
+    __syncwarp();
+  }
+}
+
+int sm_count_cached() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+void resolve_cfg(const PmScoreConfig* in, PmScoreConfig* out, bool query_device) {
+  PmScoreConfig c = {0, 0, 0, 0};
+  if (in) c = *in;
+  if (c.warps_per_block <= 0) c.warps_per_block = 8;
+  if (c.warps_per_block > 8) c.warps_per_block = 8;
+  if (c.blocks <= 0) c.blocks = 2 * (query_device ? sm_count_cached() : 148);
+  if (c.scratch_rows <= 0) c.scratch_rows = 8192;
+  *out = c;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pmnet_abi_version(void) { return PMNET_ABI_VERSION; }
+
+const char* pmnet_last_error_string(void) { return g_err; }
+
+size_t pmnet_score_workspace_bytes(int32_t n_model_nodes, int32_t n_model_clusters, const PmScoreConfig* cfg) {
+  (void)n_model_nodes;
+  PmScoreConfig c;
+  resolve_cfg(cfg, &c, cfg == nullptr || cfg->blocks <= 0);
+  const WarpLayout L = make_layout(n_model_clusters, c.scratch_rows);
+  return kHeaderBytes + (size_t)c.blocks * c.warps_per_block * L.bytes;
+}
+
+int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const float* weights, float* out_scores,
+                      float* out_conf_scores, int32_t* out_status, uint32_t* out_stats, void* workspace,
+                      size_t workspace_bytes, const PmScoreConfig* cfg, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!model || !batch || !weights) {
+    set_err("pmnet_score_batch: null argument");
+    return PMNET_EINVAL;
+  }
+  if (batch->n_ligands < 0 || model->n_nodes < 0 || model->n_clusters < 0) {
+    set_err("pmnet_score_batch: negative size");
+    return PMNET_EINVAL;
+  }
+  if (batch->n_ligands == 0) return PMNET_OK;
+  if (!out_scores || !out_status || !workspace) {
+    set_err("pmnet_score_batch: null output or workspace pointer");
+    return PMNET_EINVAL;
+  }
+  if (model->n_nodes > 255 || model->n_clusters > 255) {
+    set_err("pmnet_score_batch: model has more than 255 nodes or clusters");
+    return PMNET_ELIMIT;
+  }
+  PmScoreConfig c;
+  resolve_cfg(cfg, &c, true);
+  const size_t need = pmnet_score_workspace_bytes(model->n_nodes, model->n_clusters, &c);
+  if (workspace_bytes < need) {
+    set_err("pmnet_score_batch: workspace too small");
+    return PMNET_EWORKSPACE;
+  }
+  KernelArgs a;
+  a.model = *model;
+  a.batch = *batch;
+  for (int i = 0; i < PMNET_NUM_TYPES; ++i) a.w[i] = weights[i];
+  a.out_scores = out_scores;
+  a.out_conf = out_conf_scores;
+  a.out_status = out_status;
+  a.out_stats = out_stats;
+  a.workspace = (unsigned char*)workspace;
+  a.scratch_rows = c.scratch_rows;
+  // total model-cluster node count is needed to size shared memory; it lives on the device, so read it back once
+  int32_t n_cluster_nodes = 0;
+  cudaError_t e = cudaMemcpyAsync(&n_cluster_nodes, model->cluster_node_off + model->n_clusters, sizeof(int32_t),
+                                  cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) {
+    set_err(cudaGetErrorString(e));
+    return PMNET_ECUDA;
+  }
+  if (n_cluster_nodes < 0 || n_cluster_nodes > 65535) {
+    set_err("pmnet_score_batch: cluster_node_off is corrupt or too large");
+    return PMNET_ELIMIT;
+  }
+  a.n_cluster_nodes = n_cluster_nodes;
+  const size_t smem = smem_model_bytes(model->n_nodes, model->n_clusters, n_cluster_nodes) +
+                      (size_t)c.warps_per_block * sizeof(WarpSmem);
+  if (smem > 200 * 1024) {
+    set_err("pmnet_score_batch: model tables do not fit in shared memory");
+    return PMNET_ELIMIT;
+  }
+  e = cudaFuncSetAttribute(pmnet_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaMemsetAsync(workspace, 0, kHeaderBytes, stream);
+  if (e != cudaSuccess) {
+    set_err(cudaGetErrorString(e));
+    return PMNET_ECUDA;
+  }
+  pmnet_score_kernel<<<c.blocks, c.warps_per_block * 32, smem, stream>>>(a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_err(cudaGetErrorString(e));
+    return PMNET_ECUDA;
+  }
+  return PMNET_OK;
+}
+
+// ---------------------------------------------------------------- top-k of a shard
+__global__ void iota_ids_kernel(int64_t* ids, int64_t n, int64_t base) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ids[i] = base + i;
+}
+
+__global__ void topk_pad_kernel(const float* ks, const int64_t* vs, int64_t n, int k, float* out_s, int64_t* out_i) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k) {
+    out_s[i] = (i < n) ? ks[i] : -__int_as_float(0x7f800000);
+    out_i[i] = (i < n) ? vs[i] : -1;
+  }
+}
+
+static size_t topk_sort_bytes(int64_t n) {
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, (const float*)nullptr, (float*)nullptr,
+                                            (const int64_t*)nullptr, (int64_t*)nullptr, n);
+  return tmp;
+}
+
+size_t pmnet_topk_workspace_bytes(int64_t n, int32_t k) {
+  (void)k;
+  if (n <= 0) return 256;
+  return align_up((size_t)n * 8, 256) * 2 + align_up((size_t)n * 4, 256) + align_up(topk_sort_bytes(n), 256) + 256;
+}
+
+int pmnet_topk(const float* scores, int64_t n, int64_t id_base, int32_t k, float* out_scores, int64_t* out_ids,
+               void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || k <= 0 || !out_scores || !out_ids || (n > 0 && (!scores || !workspace))) {
+    set_err("pmnet_topk: bad argument");
+    return PMNET_EINVAL;
+  }
+  if (n > 0x7fffffffLL) {
+    set_err("pmnet_topk: more than 2^31-1 items");
+    return PMNET_ELIMIT;
+  }
+  if (workspace_bytes < pmnet_topk_workspace_bytes(n, k)) {
+    set_err("pmnet_topk: workspace too small");
+    return PMNET_EWORKSPACE;
+  }
+  float* ks = nullptr;
+  int64_t* vs = nullptr;
+  if (n > 0) {
+    unsigned char* p = (unsigned char*)workspace;
+    int64_t* ids = (int64_t*)p;  p += align_up((size_t)n * 8, 256);
+    vs = (int64_t*)p;            p += align_up((size_t)n * 8, 256);
+    ks = (float*)p;              p += align_up((size_t)n * 4, 256);
+    size_t tmp = topk_sort_bytes(n);
+    iota_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ids, n, id_base);
+    // stable LSD radix sort: equal scores keep ascending ligand id
+    cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(p, tmp, scores, ks, ids, vs, n, 0, 32, stream);
+    if (e != cudaSuccess) {
+      set_err(cudaGetErrorString(e));
+      return PMNET_ECUDA;
+    }
+  }
+  topk_pad_kernel<<<(k + 255) / 256, 256, 0, stream>>>(ks, vs, n, k, out_scores, out_ids);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_err(cudaGetErrorString(e));
+    return PMNET_ECUDA;
+  }
+  return PMNET_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,186 @@
+"""Host side of the batched scoring path: device-resident model / library containers and the C-ABI call.
+
+`score_batch` is the batched equivalent of calling the reference's `PharmacophoreModel._scoring`
+(src/pmnet/pharmacophore_model.py:101-106) once per ligand. torch is used for device memory and streams only.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _abi, _lib
+from .constants import weights_vector
+from .packing import LigandBatch, PackedModel
+
+
+def _require_cuda(device) -> torch.device:
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("pharmaconet_b200 scores on CUDA devices only (no CPU fallback)")
+    return device
+
+
+class DeviceModel:
+    """PackedModel resident in HBM + the PmModel struct pointing at it."""
+
+    def __init__(self, model: PackedModel, device="cuda"):
+        self.device = _require_cuda(device)
+        self.host = model
+        self.tensors = {k: torch.from_numpy(np.ascontiguousarray(v)).to(self.device) for k, v in model.arrays().items()}
+        self.struct = _abi.model_struct(
+            model.num_nodes, model.num_clusters, {k: t.data_ptr() for k, t in self.tensors.items()}
+        )
+
+    @property
+    def num_nodes(self) -> int:
+        return self.host.num_nodes
+
+    @property
+    def num_clusters(self) -> int:
+        return self.host.num_clusters
+
+
+class DeviceLigandBatch:
+    """LigandBatch resident in HBM (or a view into pre-allocated staging tensors) + the PmLigandBatch struct."""
+
+    def __init__(self, tensors: dict[str, torch.Tensor], n_ligands: int, n_conformers_total: int):
+        self.tensors = tensors
+        self.n_ligands = int(n_ligands)
+        self.n_conformers_total = int(n_conformers_total)
+        self.device = tensors["coords"].device
+        self.struct = _abi.batch_struct(self.n_ligands, {k: tensors[k].data_ptr() for k in _abi.BATCH_FIELDS})
+
+    @classmethod
+    def from_host(cls, batch: LigandBatch, device="cuda", non_blocking: bool = False) -> "DeviceLigandBatch":
+        device = _require_cuda(device)
+        t = {
+            k: torch.from_numpy(np.ascontiguousarray(v)).to(device, non_blocking=non_blocking)
+            for k, v in batch.arrays().items()
+        }
+        return cls(t, batch.num_ligands, batch.num_conformers_total)
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.tensors.values())
+
+
+@dataclass
+class ScoreConfig:
+    warps_per_block: int = 0  # 0 = library default
+    blocks: int = 0
+    scratch_rows: int = 0
+
+    def struct(self) -> _abi.PmScoreConfig:
+        return _abi.PmScoreConfig(self.warps_per_block, self.blocks, self.scratch_rows, 0)
+
+
+# a second, roomier configuration for ligands whose pair table overflowed the default per-warp scratch
+BIG_CONFIG = ScoreConfig(warps_per_block=4, blocks=148, scratch_rows=262144)
+
+_workspaces: dict[tuple, torch.Tensor] = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(),)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def release_workspaces() -> None:
+    _workspaces.clear()
+
+
+def score_batch(
+    model: DeviceModel,
+    batch: DeviceLigandBatch,
+    weights: dict[str, float] | None = None,
+    config: ScoreConfig | None = None,
+    out_scores: torch.Tensor | None = None,
+    out_status: torch.Tensor | None = None,
+    with_stats: bool = False,
+    with_conf: bool = False,
+    stream: torch.cuda.Stream | None = None,
+):
+    """Enqueue one scoring launch on `stream` (default: torch's current stream). Returns a dict of device tensors:
+    scores f32[n], status i32[n] (+ stats u32[n,4] -> {tree nodes, leaves, rows, pair entries}; conf f32[n,32])."""
+    L = _lib.lib()
+    dev = model.device
+    n = batch.n_ligands
+    cfg = (config or ScoreConfig()).struct()
+    with torch.cuda.device(dev):
+        need = L.pmnet_score_workspace_bytes(model.num_nodes, model.num_clusters, C.byref(cfg))
+        ws = _workspace(dev, need)
+        scores = out_scores if out_scores is not None else torch.empty(n, dtype=torch.float32, device=dev)
+        status = out_status if out_status is not None else torch.empty(n, dtype=torch.int32, device=dev)
+        stats = torch.zeros((n, 4), dtype=torch.int32, device=dev) if with_stats else None
+        conf = torch.zeros((n, 32), dtype=torch.float32, device=dev) if with_conf else None
+        w = (C.c_float * 7)(*weights_vector(weights))
+        s = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = L.pmnet_score_batch(
+            C.byref(model.struct), C.byref(batch.struct), w, scores.data_ptr(),
+            conf.data_ptr() if with_conf else None, status.data_ptr(), stats.data_ptr() if with_stats else None,
+            ws.data_ptr(), ws.numel(), C.byref(cfg), C.c_void_p(s.cuda_stream),
+        )  # fmt: skip
+        _lib.check(rc, "pmnet_score_batch")
+    out = dict(scores=scores, status=status)
+    if with_stats:
+        out["stats"] = stats
+    if with_conf:
+        out["conf"] = conf
+    return out
+
+
+def score_library(
+    model: DeviceModel,
+    host_batch: LigandBatch,
+    weights: dict[str, float] | None = None,
+    config: ScoreConfig | None = None,
+    with_stats: bool = False,
+) -> dict[str, np.ndarray]:
+    """Score a host-resident library chunk: H2D, one launch, re-run of overflowed ligands with BIG_CONFIG, D2H.
+    Returns numpy arrays (scores f32, status i32[, stats])."""
+    dev_batch = DeviceLigandBatch.from_host(host_batch, model.device)
+    out = score_batch(model, dev_batch, weights, config, with_stats=with_stats)
+    scores = out["scores"].cpu().numpy()
+    status = out["status"].cpu().numpy()
+    stats = out["stats"].cpu().numpy().view(np.uint32) if with_stats else None
+    over = np.nonzero(status == _abi.LIG_OVERFLOW)[0]
+    if len(over):
+        sub = host_batch.select(over)
+        o2 = score_batch(model, DeviceLigandBatch.from_host(sub, model.device), weights, BIG_CONFIG, with_stats=with_stats)
+        scores[over] = o2["scores"].cpu().numpy()
+        status[over] = o2["status"].cpu().numpy()
+        if with_stats:
+            stats[over] = o2["stats"].cpu().numpy().view(np.uint32)
+    res = dict(scores=scores, status=status)
+    if with_stats:
+        res["stats"] = stats
+    return res
+
+
+def topk(scores: torch.Tensor, k: int, id_base: int = 0, stream: torch.cuda.Stream | None = None):
+    """k best (score, id_base + index) of a device score vector, descending, ties by ascending id."""
+    L = _lib.lib()
+    dev = scores.device
+    _require_cuda(dev)
+    n = scores.numel()
+    with torch.cuda.device(dev):
+        need = L.pmnet_topk_workspace_bytes(n, k)
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        out_s = torch.empty(k, dtype=torch.float32, device=dev)
+        out_i = torch.empty(k, dtype=torch.int64, device=dev)
+        s = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = L.pmnet_topk(
+            scores.data_ptr(), n, int(id_base), int(k), out_s.data_ptr(), out_i.data_ptr(), ws.data_ptr(), need,
+            C.c_void_p(s.cuda_stream),
+        )  # fmt: skip
+        _lib.check(rc, "pmnet_topk")
+        # ws must outlive the enqueued kernels
+        s.synchronize()
+    return out_s, out_i

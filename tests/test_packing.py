@@ -1,0 +1,40 @@
+"""Host featuriser / packed formats against the reference-built golden batches (no GPU)."""
+
+import numpy as np
+import pytest
+from golden_util import CASES, load_case
+
+from pharmaconet_b200 import synthetic
+from pharmaconet_b200.packing import LigandBatch
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_host_featuriser_reproduces_reference_graphs(name):
+    # golden lig_* arrays were packed from the reference's own LigandGraph objects (ligand.py:110-259)
+    c = load_case(name)
+    ligs = synthetic.make_ligands(**c["gen_kwargs"])
+    own = LigandBatch.from_typed(ligs)
+    for k, v in c["batch"].arrays().items():
+        assert np.array_equal(v, own.arrays()[k]), k
+
+
+def test_select_roundtrip():
+    c = load_case("syn0_c8")
+    b = c["batch"]
+    idx = [5, 0, 17, 17, 100]
+    sub = b.select(idx)
+    assert sub.num_ligands == 5
+    for j, i in enumerate(idx):
+        s0, s1 = sub.coord_off[j], sub.coord_off[j + 1]
+        t0, t1 = b.coord_off[i], b.coord_off[i + 1]
+        assert np.array_equal(sub.coords[s0:s1], b.coords[t0:t1])
+        assert sub.n_conf[j] == b.n_conf[i]
+    assert sub.select(range(5)).coords.tobytes() == sub.coords.tobytes()
+
+
+def test_coord_layout_alignment():
+    c = load_case("syn0_c5_big")
+    b = c["batch"]
+    assert np.all(b.coord_off % 4 == 0)
+    stride = (b.n_conf + 3) // 4 * 4
+    assert np.array_equal(np.diff(b.coord_off), np.diff(b.lig_node_off) * 3 * stride)

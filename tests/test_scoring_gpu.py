@@ -1,0 +1,123 @@
+"""Parity of the CUDA scoring kernel (through the C-ABI) with the reference golden vectors and the CPU oracle."""
+
+import numpy as np
+import pytest
+import torch
+from golden_util import CASES, load_case, rel_err, weights_dict
+
+import oracle as orc
+from pharmaconet_b200 import _abi, scoring, synthetic
+from pharmaconet_b200.packing import LigandBatch
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5  # BASELINE.json north_star: scores within 1e-5 relative of the reference
+
+
+def _run(model, batch, weights, **kw):
+    dm = scoring.DeviceModel(model, "cuda:0")
+    return scoring.score_library(dm, batch, weights_dict(weights) if weights is not None else None, with_stats=True, **kw)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_kernel_matches_reference_golden(name):
+    c = load_case(name)
+    out = _run(c["model"], c["batch"], c["weights"])
+    assert np.all(out["status"] <= _abi.LIG_EMPTY)
+    assert rel_err(out["scores"], c["ref"]).max() <= REL_TOL
+    # exact zeros where the reference returns 0 (no candidates)
+    assert np.array_equal(out["scores"] == 0.0, c["ref"] == 0.0)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_kernel_tree_shape_identical_to_oracle(name):
+    # all discrete decisions are meant to be bit-identical: same number of tree nodes and leaves per ligand
+    c = load_case(name)
+    out = _run(c["model"], c["batch"], c["weights"])
+    o = orc.score(c["model"], c["batch"], c["weights"])
+    assert np.array_equal(out["status"], o["status"])
+    assert np.array_equal(out["stats"][:, 0].astype(np.uint64), o["stats"][:, 0])
+    assert np.array_equal(out["stats"][:, 1].astype(np.uint64), o["stats"][:, 1])
+    assert np.array_equal(out["stats"][:, 3].astype(np.uint64), o["stats"][:, 3])
+
+
+@pytest.mark.parametrize("nconf,n,seed", [(32, 4096, 101), (8, 2048, 102), (13, 1024, 103)])
+def test_kernel_matches_oracle_fresh_inputs(nconf, n, seed):
+    c = load_case("syn0_c32")
+    batch = LigandBatch.from_typed(synthetic.make_ligands(n, nconf, seed=seed))
+    out = _run(c["model"], batch, None)
+    o = orc.score(c["model"], batch, None)
+    assert np.array_equal(out["status"], o["status"])
+    assert rel_err(out["scores"], o["scores"]).max() <= REL_TOL
+    assert np.array_equal(out["stats"][:, 0].astype(np.uint64), o["stats"][:, 0])
+
+
+def test_per_conformer_scores_match_oracle():
+    c = load_case("syn0_c8")
+    dm = scoring.DeviceModel(c["model"], "cuda:0")
+    out = scoring.score_batch(dm, scoring.DeviceLigandBatch.from_host(c["batch"], "cuda:0"), with_conf=True)
+    conf = out["conf"].cpu().numpy()[:, :8]
+    o = orc.score(c["model"], c["batch"], c["weights"], with_conf=True)
+    assert np.abs(conf - o["conf"][:, :8]).max() <= REL_TOL * max(1.0, np.abs(o["conf"]).max())
+
+
+def test_ligand_order_invariance_bit_exact():
+    c = load_case("syn0_c32")
+    b = c["batch"]
+    perm = np.random.default_rng(0).permutation(b.num_ligands)
+    a = _run(c["model"], b, None)["scores"]
+    p = _run(c["model"], b.select(perm), None)["scores"]
+    assert np.array_equal(a[perm], p)
+
+
+def test_identical_conformers_equal_single_conformer():
+    c = load_case("syn0_c1")
+    ligs = synthetic.make_ligands(**c["gen_kwargs"])
+    for lig in ligs:
+        lig.atom_positions = np.repeat(lig.atom_positions, 32, axis=1)
+    rep = LigandBatch.from_typed(ligs)
+    a = _run(c["model"], c["batch"], None)["scores"]
+    r = _run(c["model"], rep, None)["scores"]
+    assert rel_err(r, a).max() <= 1e-6
+
+
+def test_overflow_is_reported_and_rerun():
+    c = load_case("syn0_c5_big")
+    dm = scoring.DeviceModel(c["model"], "cuda:0")
+    db = scoring.DeviceLigandBatch.from_host(c["batch"], "cuda:0")
+    tiny = scoring.ScoreConfig(warps_per_block=4, blocks=8, scratch_rows=64)
+    st = scoring.score_batch(dm, db, config=tiny)["status"].cpu().numpy()
+    assert (st == _abi.LIG_OVERFLOW).sum() > 0
+    out = scoring.score_library(dm, c["batch"], config=tiny)
+    assert np.all(out["status"] == _abi.LIG_OK)
+    assert rel_err(out["scores"], c["ref"]).max() <= REL_TOL
+
+
+def test_launch_geometry_does_not_change_results():
+    c = load_case("syn0_c8")
+    a = _run(c["model"], c["batch"], None)["scores"]
+    for cfg in (scoring.ScoreConfig(1, 3, 4096), scoring.ScoreConfig(8, 296, 2048), scoring.ScoreConfig(4, 1, 8192)):
+        b = _run(c["model"], c["batch"], None, config=cfg)["scores"]
+        assert np.array_equal(a, b)
+
+
+def test_empty_batch_and_bad_args():
+    c = load_case("syn0_c8")
+    dm = scoring.DeviceModel(c["model"], "cuda:0")
+    out = scoring.score_library(dm, c["batch"].select([]))
+    assert out["scores"].shape == (0,)
+    with pytest.raises(RuntimeError):
+        scoring.DeviceModel(c["model"], "cpu")
+
+
+def test_topk_matches_sort():
+    g = torch.Generator(device="cpu").manual_seed(0)
+    s = torch.rand(100003, generator=g)
+    s[::7] = s[3]  # ties
+    sd = s.cuda()
+    ks, ki = scoring.topk(sd, 1000, id_base=5000)
+    order = np.lexsort((np.arange(s.numel()), -s.numpy()))[:1000]
+    assert np.array_equal(ki.cpu().numpy(), order + 5000)
+    assert np.array_equal(ks.cpu().numpy(), s.numpy()[order])
+    ks2, ki2 = scoring.topk(sd[:10], 16)
+    assert np.all(ki2.cpu().numpy()[10:] == -1) and np.all(np.isinf(ks2.cpu().numpy()[10:]))
