@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py - the driver's benchmark contract for the screening hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): a synthetic "6OIM-like" pharmacophore model (35 nodes / 26 clusters, built by
+the reference's own PharmacophoreModel.create, shipped as tests/golden/model_syn0.pm) against a seeded synthetic
+library of 1 M typed ligands x 32 conformers PER GPU (weak scaling). One "step" = one full pass of the scoring path
+over the rank's library + per-rank top-k + (N > 1) one NCCL all-gather of the top-k and the merge.
+
+  value  : conformers/s, whole job, library already resident in HBM        (CUDA events, max over ranks)
+  e2e    : the same through Screener.screen_host with PINNED HOST buffers: every step copies the whole library
+           host->device (double-buffered blocks) and the scores/status/top-k device->host inside the timed region
+  roofline: HBM - algorithmic bytes of one scoring launch / its CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline: the CPU oracle (a C port of the reference's algorithm, oracle/pmnet_oracle.c - kind "port") on all
+           host cores over a bounded prefix of the same library, also used as a live parity check of the GPU scores
+
+`--impl reference` times that CPU port alone (rank 0 only), one bounded sample of the same workload per step.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "ligand_conformers_scored_per_sec"
+UNIT = "conformers/s"
+SAMPLE_LIGANDS = 4096  # ligands per reference step / cpu_baseline block
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ligands", type=int, default=1_000_000, help="ligands per GPU")
+    ap.add_argument("--conformers", type=int, default=32)
+    ap.add_argument("--templates", type=int, default=4096)
+    ap.add_argument("--topk", type=int, default=1000)
+    ap.add_argument("--block-ligands", type=int, default=65536)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic():
+    """dram bytes per scoring launch from the committed ncu --set full capture, if there is one."""
+    path = os.path.join(ROOT, "profiles", "scoring_kernel_latest.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
+
+
+class ClockSampler:
+    QUERY = (
+        "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+        "clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.path = f"/tmp/pmnet_clocks_{os.getpid()}.csv"
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                stdout=self.f, stderr=subprocess.DEVNULL,
+            )  # fmt: skip
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"6OIM-like synthetic model (35 nodes/26 clusters) x {args.ligands} synthetic ligands x "
+        f"{args.conformers} conformers per GPU (BASELINE configs[1])",
+        "ligands_per_gpu": args.ligands,
+        "conformers_per_ligand": args.conformers,
+        "templates": args.templates,
+        "topk": args.topk,
+        "parallelism": f"ligand-sharded x{world}, one NCCL all-gather of top-k per step",
+        "l2_policy": "inputs larger than L2 (library coordinates >> 126 MB per pass)",
+    }
+
+
+def host_prefix(dev_lib, n):
+    """First n ligands of a device library as a host LigandBatch (for the CPU port)."""
+    import numpy as np
+
+    from pharmaconet_b200.packing import LigandBatch
+
+    t = dev_lib.tensors
+    n = min(n, dev_lib.n_ligands)
+    nn = int(t["lig_node_off"][n])
+    nq = int(t["lig_cluster_off"][n])
+    ncn = int(t["cluster_node_off"][nq])
+    nx = int(t["coord_off"][n])
+    return LigandBatch.from_arrays(
+        dict(
+            lig_node_off=t["lig_node_off"][: n + 1].cpu().numpy(),
+            lig_cluster_off=t["lig_cluster_off"][: n + 1].cpu().numpy(),
+            cluster_node_off=t["cluster_node_off"][: nq + 1].cpu().numpy(),
+            cluster_nodes=t["cluster_nodes"][:ncn].cpu().numpy(),
+            node_type_mask=t["node_type_mask"][:nn].cpu().numpy(),
+            n_conf=t["n_conf"][:n].cpu().numpy(),
+            coord_off=t["coord_off"][: n + 1].cpu().numpy(),
+            coords=t["coords"][:nx].cpu().numpy(),
+        )
+    )
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path = the C port in oracle/ on all host cores."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+
+    import oracle as orc
+    from pharmaconet_b200 import synthetic
+    from pharmaconet_b200.packing import LigandBatch, PackedModel
+    from pharmaconet_b200.pharmacophore_model import PharmacophoreModel
+
+    packed = PackedModel.from_model(PharmacophoreModel.load(os.path.join(ROOT, "tests", "golden", "model_syn0.pm")))
+    if torch.cuda.is_available():
+        lib = synthetic.make_library_device(args.ligands, args.conformers, args.seed, "cuda:0", args.templates)
+        sample = host_prefix(lib, SAMPLE_LIGANDS)
+        del lib
+        torch.cuda.empty_cache()
+    else:
+        sample = LigandBatch.from_typed(synthetic.make_ligands(SAMPLE_LIGANDS, args.conformers, args.seed))
+    cores = orc.max_threads()
+    n_conf = sample.num_conformers_total
+    for _ in range(args.warmup):
+        orc.score(packed, sample, threads=cores, end=min(256, sample.num_ligands))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.score(packed, sample, threads=cores)
+    dt = time.perf_counter() - t0
+    value = n_conf * args.steps / dt
+    cfg = workload_config(args, world)
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {
+            "value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {sample.num_ligands} ligands x {args.conformers} conformers of the workload per step",
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }  # fmt: skip
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from pharmaconet_b200 import screening, synthetic
+    from pharmaconet_b200.packing import LigandBatch, PackedModel
+    from pharmaconet_b200.pharmacophore_model import PharmacophoreModel
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the scoring path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    packed = PackedModel.from_model(PharmacophoreModel.load(os.path.join(ROOT, "tests", "golden", "model_syn0.pm")))
+    lib = synthetic.make_library_device(args.ligands, args.conformers, args.seed + rank, dev, args.templates)
+    n_lig, n_conf = lib.n_ligands, lib.n_conformers_total
+    alg_bytes = lib.nbytes() + 4 * n_lig  # every input array once + one fp32 score per ligand
+    scr = screening.Screener(packed, dev, k=args.topk, block_ligands=args.block_ligands)
+    id_base = rank * n_lig
+
+    # ---------------------------------------------------------------- leg 1: library resident in HBM
+    for _ in range(args.warmup):
+        res = scr.screen_device(lib, id_base)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    scr.record_kernel_events = True
+    scr.kernel_events.clear()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    e0.record()
+    for _ in range(args.steps):
+        res = scr.screen_device(lib, id_base)
+        launches += res.launches
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    kernel_ms = [a.elapsed_time(b) for a, b in scr.kernel_events]
+    scr.record_kernel_events = False
+    kernel_ms_avg = max_over_ranks(sum(kernel_ms) / len(kernel_ms))
+    value = world * n_conf * args.steps / (ms_total * 1e-3)
+    gpu_scores = res.scores  # device tensor, this rank
+    top_ids = res.topk_ids.cpu().numpy()
+
+    # ---------------------------------------------------------------- leg 2: end to end from pinned host memory
+    e2e = None
+    if not args.no_e2e:
+        host = LigandBatch.from_arrays({k: v.cpu().numpy() for k, v in lib.tensors.items()})
+        host = screening.pin_library(host)
+        h2d = sum(v.nbytes for v in host.arrays().values())
+        d2h = n_lig * 8 + args.topk * 12
+        del lib
+        torch.cuda.empty_cache()
+        for _ in range(max(1, args.warmup)):
+            r2 = scr.screen_host(host)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            r2 = scr.screen_host(host)
+        e1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
+        e2e = {
+            "value": world * n_conf * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+            "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * d2h,
+            "ms_per_step": ms_e2e / args.steps, "api": "pharmaconet_b200.screening.Screener.screen_host",
+            "n_overflow_rerun": r2.n_overflow,
+        }  # fmt: skip
+        same = bool(np.array_equal(r2.scores, gpu_scores.cpu().numpy()))
+        e2e["scores_identical_to_resident_leg"] = same
+    else:
+        host = None
+
+    # ---------------------------------------------------------------- leg 3: CPU port on a bounded prefix (rank 0, N = 1)
+    cpu_baseline = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle as orc
+
+        cores = orc.max_threads()
+        src = host if host is not None else None
+        if src is None:
+            src = LigandBatch.from_arrays({k: v.cpu().numpy() for k, v in lib.tensors.items()})
+        orc.score(packed, src, threads=cores, end=min(256, n_lig))  # warm-up
+        done, t0 = 0, time.perf_counter()
+        ref_scores = []
+        while done < n_lig and time.perf_counter() - t0 < args.cpu_seconds:
+            end = min(n_lig, done + SAMPLE_LIGANDS)
+            ref_scores.append(orc.score(packed, src, threads=cores, begin=done, end=end)["scores"])
+            done = end
+        dt = time.perf_counter() - t0
+        ref_scores = np.concatenate(ref_scores)
+        cpu_baseline = {
+            "value": done * args.conformers / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {done} ligands x {args.conformers} conformers of the same library ({dt:.1f} s)",
+        }  # fmt: skip
+        g = gpu_scores[:done].cpu().numpy().astype(np.float64)
+        rel = np.abs(g - ref_scores) / np.maximum(np.abs(ref_scores), 1e-12)
+        parity = {"checked_ligands": int(done), "max_rel_err_vs_cpu_port": float(rel.max()), "tolerance": 1e-5}
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        achieved = alg_bytes / (kernel_ms_avg * 1e-3) / 1e9
+        prof = load_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": e2e, "gpu_launches": launches,
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (prof or {}).get("dram_bytes_per_launch"),
+                "kernel": "pmnet_score_kernel", "kernel_ms_avg": kernel_ms_avg,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "note": "the path is instruction-issue bound, not HBM bound (DESIGN.md section 5): the HBM fraction "
+                        "is reported because BASELINE.json asks for it",
+            },
+            "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,
+            "top1": {"id": int(top_ids[0]), "score": float(res.topk_scores[0].item())},
+        }  # fmt: skip
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -67,6 +67,8 @@ enum {
 typedef struct PmModel {
   int32_t n_nodes;                 /* Nm <= 255 */
   int32_t n_clusters;              /* Km <= 255 */
+  int32_t n_cluster_nodes;         /* = cluster_node_off[Km] (host copy, so that no device read-back is needed) */
+  int32_t reserved;
   const uint8_t* node_type;        /* [Nm]     pharmacophore type index 0..6 of each model node */
   const float* edge_mu;            /* [Nm*Nm]  ModelEdge.distance_mean as fp32 */
   const float* edge_sigma;         /* [Nm*Nm]  ModelEdge.distance_std  as fp32 */
@@ -92,6 +94,14 @@ typedef struct PmLigandBatch {
   const int32_t* n_conf;           /* [n] conformers per ligand, 1..PMNET_MAX_CONFORMERS */
   const int64_t* coord_off;        /* [n+1] in floats */
   const float* coords;             /* fp32 node coordinates (LigandNode.positions, ligand.py:293-301) */
+  /* A chunk of a larger library can be passed without re-basing its CSR offsets: the values stored in the
+   * offset arrays are relative to these bases (0 for a self-contained batch), i.e. the data arrays passed here
+   * start at node `node_base`, cluster `cluster_base`, cluster-node `cnode_base`, float `coord_base`. */
+  int64_t coord_base;
+  int32_t node_base;
+  int32_t cluster_base;
+  int32_t cnode_base;
+  int32_t reserved;
 } PmLigandBatch;
 
 /* Launch configuration; zero-initialise for defaults. */

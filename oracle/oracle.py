@@ -57,7 +57,9 @@ def score(model, batch, weights=None, threads: int = 0, begin: int = 0, end: int
     n = end - begin
     marr = {k: np.ascontiguousarray(v) for k, v in model.arrays().items()}
     barr = {k: np.ascontiguousarray(v) for k, v in batch.arrays().items()}
-    ms = _abi.model_struct(model.num_nodes, model.num_clusters, {k: v.ctypes.data for k, v in marr.items()})
+    ms = _abi.model_struct(
+        model.num_nodes, model.num_clusters, int(model.cluster_node_off[-1]), {k: v.ctypes.data for k, v in marr.items()}
+    )
     bs = _abi.batch_struct(batch.num_ligands, {k: v.ctypes.data for k, v in barr.items()})
     w = np.asarray(weights_vector(weights) if not isinstance(weights, np.ndarray) else weights, dtype=np.float32)
     scores = np.zeros(n, dtype=np.float64)

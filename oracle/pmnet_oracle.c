@@ -240,16 +240,17 @@ static int score_one(const PmModel* md, const PmLigandBatch* b, const float* w, 
   *out_score = 0.0;
   if (x.C < 1 || x.C > MAXC) return PMNET_LIG_UNSUPPORTED;
   x.stride = (x.C + 3) & ~3;
-  x.xyz = b->coords + b->coord_off[lig];
-  const uint8_t* tmask = b->node_type_mask + b->lig_node_off[lig];
-  const int q0 = b->lig_cluster_off[lig], q1 = b->lig_cluster_off[lig + 1];
+  x.xyz = b->coords + (b->coord_off[lig] - b->coord_base);
+  const uint8_t* tmask = b->node_type_mask + (b->lig_node_off[lig] - b->node_base);
+  const int q0 = b->lig_cluster_off[lig] - b->cluster_base, q1 = b->lig_cluster_off[lig + 1] - b->cluster_base;
+  const uint8_t* cl_nodes = b->cluster_nodes - b->cnode_base; /* indexed with the stored (un-rebased) offsets */
   const int Km = md->n_clusters;
 
   /* levels = clusters with >= 1 candidate model cluster, in priority order, first 20 (graph_match.py:85-88) */
   uint8_t lev_mask[MAXLEV];
   for (int q = q0; q < q1 && x.L < MAXLEV; ++q) {
     uint8_t m = 0;
-    for (int i = b->cluster_node_off[q]; i < b->cluster_node_off[q + 1]; ++i) m |= tmask[b->cluster_nodes[i]];
+    for (int i = b->cluster_node_off[q]; i < b->cluster_node_off[q + 1]; ++i) m |= tmask[cl_nodes[i]];
     int any = 0;
     for (int k = 0; k < Km; ++k) any |= (md->cluster_mask[k] & m) != 0;
     if (any) {
@@ -286,7 +287,7 @@ static int score_one(const PmModel* md, const PmLigandBatch* b, const float* w, 
     MatchList* ml = &x.ent_match[e];
     ml->nm = (NodeMatch*)malloc(sizeof(NodeMatch) * (nn > 0 ? nn : 1));
     for (int i = 0; i < nn; ++i) {
-      const int node = b->cluster_nodes[b->cluster_node_off[q] + i];
+      const int node = cl_nodes[b->cluster_node_off[q] + i];
       NodeMatch t;
       t.node = node;
       t.n = 0;
@@ -314,7 +315,7 @@ static int score_one(const PmModel* md, const PmLigandBatch* b, const float* w, 
   float* size = (float*)malloc(sizeof(float) * x.L * C);
   for (int l = 0; l < x.L; ++l) {
     const int q = x.lev_cluster[l];
-    cluster_geometry(&x, b->cluster_nodes + b->cluster_node_off[q], b->cluster_node_off[q + 1] - b->cluster_node_off[q],
+    cluster_geometry(&x, cl_nodes + b->cluster_node_off[q], b->cluster_node_off[q + 1] - b->cluster_node_off[q],
                      ctr + (size_t)l * C * 3, size + (size_t)l * C);
   }
   uint64_t n_pair_entries = 0;

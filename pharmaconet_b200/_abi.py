@@ -20,6 +20,8 @@ class PmModel(C.Structure):
     _fields_ = [
         ("n_nodes", C.c_int32),
         ("n_clusters", C.c_int32),
+        ("n_cluster_nodes", C.c_int32),
+        ("reserved", C.c_int32),
         ("node_type", C.c_void_p),
         ("edge_mu", C.c_void_p),
         ("edge_sigma", C.c_void_p),
@@ -42,6 +44,11 @@ class PmLigandBatch(C.Structure):
         ("n_conf", C.c_void_p),
         ("coord_off", C.c_void_p),
         ("coords", C.c_void_p),
+        ("coord_base", C.c_int64),
+        ("node_base", C.c_int32),
+        ("cluster_base", C.c_int32),
+        ("cnode_base", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -76,18 +83,21 @@ BATCH_FIELDS = (
 )
 
 
-def model_struct(n_nodes: int, n_clusters: int, ptrs: dict[str, int]) -> PmModel:
+def model_struct(n_nodes: int, n_clusters: int, n_cluster_nodes: int, ptrs: dict[str, int]) -> PmModel:
     """ptrs: field name -> raw address (host or device, the callee decides what it expects)."""
     m = PmModel()
-    m.n_nodes, m.n_clusters = int(n_nodes), int(n_clusters)
+    m.n_nodes, m.n_clusters, m.n_cluster_nodes = int(n_nodes), int(n_clusters), int(n_cluster_nodes)
     for f in MODEL_FIELDS:
         setattr(m, f, int(ptrs[f]) or None)
     return m
 
 
-def batch_struct(n_ligands: int, ptrs: dict[str, int]) -> PmLigandBatch:
+def batch_struct(n_ligands: int, ptrs: dict[str, int], bases: dict[str, int] | None = None) -> PmLigandBatch:
+    """bases: optional {coord_base, node_base, cluster_base, cnode_base} for a chunk view of a larger library."""
     b = PmLigandBatch()
     b.n_ligands = int(n_ligands)
     for f in BATCH_FIELDS:
         setattr(b, f, int(ptrs[f]) or None)
+    for k, v in (bases or {}).items():
+        setattr(b, k, int(v))
     return b

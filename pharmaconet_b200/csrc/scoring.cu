@@ -246,9 +246,10 @@ __global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args)
       status = PMNET_LIG_UNSUPPORTED;
     } else {
       const int stride = (C + 3) & ~3;
-      const float* xyz = B.coords + B.coord_off[lig];
-      const uint8_t* tmask = B.node_type_mask + B.lig_node_off[lig];
-      const int q0 = B.lig_cluster_off[lig], q1 = B.lig_cluster_off[lig + 1];
+      const float* xyz = B.coords + (B.coord_off[lig] - B.coord_base);
+      const uint8_t* tmask = B.node_type_mask + (B.lig_node_off[lig] - B.node_base);
+      const int q0 = B.lig_cluster_off[lig] - B.cluster_base, q1 = B.lig_cluster_off[lig + 1] - B.cluster_base;
+      const uint8_t* cl_nodes = B.cluster_nodes - B.cnode_base;  // indexed with the stored (un-rebased) offsets
       const bool on = lane < C;
       const unsigned cmask_full = (C == 32) ? kFull : ((1u << C) - 1u);
 
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args)
       for (int q = q0; q < q1 && L < kMaxDepth && !overflow; ++q) {
         const int c0 = B.cluster_node_off[q], c1 = B.cluster_node_off[q + 1];
         unsigned m = 0;
-        for (int i = c0 + lane; i < c1; i += 32) m |= tmask[B.cluster_nodes[i]];
+        for (int i = c0 + lane; i < c1; i += 32) m |= tmask[cl_nodes[i]];
         m = __reduce_or_sync(kFull, m);
         int t_level = T;
         for (int k0 = 0; k0 < KM; k0 += 32) {
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args)
           const int n = c1 - c0;
           float cx = 0.f, cy = 0.f, cz = 0.f;
           for (int i = c0; i < c1; ++i) {
-            const int node = B.cluster_nodes[i];
+            const int node = cl_nodes[i];
             const float x = ld_coord(xyz, stride, node, 0, lane, on), y = ld_coord(xyz, stride, node, 1, lane, on),
                         z = ld_coord(xyz, stride, node, 2, lane, on);
             if (i == c0) {
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args)
           cx = __fdiv_rn(cx, fn); cy = __fdiv_rn(cy, fn); cz = __fdiv_rn(cz, fn);
           float sz = 0.f;
           for (int i = c0; i < c1; ++i) {
-            const int node = B.cluster_nodes[i];
+            const int node = cl_nodes[i];
             const float d = norm3(__fsub_rn(ld_coord(xyz, stride, node, 0, lane, on), cx),
                                   __fsub_rn(ld_coord(xyz, stride, node, 1, lane, on), cy),
                                   __fsub_rn(ld_coord(xyz, stride, node, 2, lane, on), cz));
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args)
             q = ws.lev_q[entlev[e]];
             k = entmc[e];
             for (int i = B.cluster_node_off[q]; i < B.cluster_node_off[q + 1]; ++i) {
-              const unsigned tm = tmask[B.cluster_nodes[i]];
+              const unsigned tm = tmask[cl_nodes[i]];
               int M = 0;
               for (int j = sm.cnode_off[k]; j < sm.cnode_off[k + 1]; ++j) M += (tm >> sm.ntype[sm.cnodes[j]]) & 1u;
               if (M > kMaxClusterNodes) toobig = true;
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args)
             nmoff[e] = o;
             nmcnt[e] = (uint8_t)cnt;
             for (int i = B.cluster_node_off[q]; i < B.cluster_node_off[q + 1]; ++i) {
-              const int node = B.cluster_nodes[i];
+              const int node = cl_nodes[i];
               const unsigned tm = tmask[node];
               int M = 0;
               for (int j = sm.cnode_off[k]; j < sm.cnode_off[k + 1]; ++j) {
@@ -718,19 +719,12 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
   a.out_stats = out_stats;
   a.workspace = (unsigned char*)workspace;
   a.scratch_rows = c.scratch_rows;
-  // total model-cluster node count is needed to size shared memory; it lives on the device, so read it back once
-  int32_t n_cluster_nodes = 0;
-  cudaError_t e = cudaMemcpyAsync(&n_cluster_nodes, model->cluster_node_off + model->n_clusters, sizeof(int32_t),
-                                  cudaMemcpyDeviceToHost, stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-  if (e != cudaSuccess) {
-    set_err(cudaGetErrorString(e));
-    return PMNET_ECUDA;
-  }
+  const int32_t n_cluster_nodes = model->n_cluster_nodes;
   if (n_cluster_nodes < 0 || n_cluster_nodes > 65535) {
-    set_err("pmnet_score_batch: cluster_node_off is corrupt or too large");
+    set_err("pmnet_score_batch: n_cluster_nodes out of range");
     return PMNET_ELIMIT;
   }
+  cudaError_t e;
   a.n_cluster_nodes = n_cluster_nodes;
   const size_t smem = smem_model_bytes(model->n_nodes, model->n_clusters, n_cluster_nodes) +
                       (size_t)c.warps_per_block * sizeof(WarpSmem);

@@ -32,7 +32,10 @@ class DeviceModel:
         self.host = model
         self.tensors = {k: torch.from_numpy(np.ascontiguousarray(v)).to(self.device) for k, v in model.arrays().items()}
         self.struct = _abi.model_struct(
-            model.num_nodes, model.num_clusters, {k: t.data_ptr() for k, t in self.tensors.items()}
+            model.num_nodes,
+            model.num_clusters,
+            int(model.cluster_node_off[-1]),
+            {k: t.data_ptr() for k, t in self.tensors.items()},
         )
 
     @property
@@ -47,12 +50,21 @@ class DeviceModel:
 class DeviceLigandBatch:
     """LigandBatch resident in HBM (or a view into pre-allocated staging tensors) + the PmLigandBatch struct."""
 
-    def __init__(self, tensors: dict[str, torch.Tensor], n_ligands: int, n_conformers_total: int):
+    def __init__(
+        self,
+        tensors: dict[str, torch.Tensor],
+        n_ligands: int,
+        n_conformers_total: int,
+        bases: dict[str, int] | None = None,
+    ):
+        """bases: for a block of a larger library whose CSR offsets were not re-based (see include/pmnet_b200.h)."""
         self.tensors = tensors
         self.n_ligands = int(n_ligands)
         self.n_conformers_total = int(n_conformers_total)
         self.device = tensors["coords"].device
-        self.struct = _abi.batch_struct(self.n_ligands, {k: tensors[k].data_ptr() for k in _abi.BATCH_FIELDS})
+        self.struct = _abi.batch_struct(
+            self.n_ligands, {k: tensors[k].data_ptr() for k in _abi.BATCH_FIELDS}, bases
+        )
 
     @classmethod
     def from_host(cls, batch: LigandBatch, device="cuda", non_blocking: bool = False) -> "DeviceLigandBatch":
@@ -77,8 +89,13 @@ class ScoreConfig:
         return _abi.PmScoreConfig(self.warps_per_block, self.blocks, self.scratch_rows, 0)
 
 
-# a second, roomier configuration for ligands whose pair table overflowed the default per-warp scratch
-BIG_CONFIG = ScoreConfig(warps_per_block=4, blocks=148, scratch_rows=262144)
+def big_config(model) -> ScoreConfig:
+    """A roomy configuration for ligands whose pair table overflowed the default per-warp scratch: rows for the
+    worst case of this model (T = min(20 Km, 1024) entries, T^2/2 pairs), on fewer warps."""
+    t = min(20 * model.num_clusters, 1024)
+    rows = max(8192, t * t // 2 + t)
+    return ScoreConfig(warps_per_block=4, blocks=32, scratch_rows=rows)
+
 
 _workspaces: dict[tuple, torch.Tensor] = {}
 
@@ -153,7 +170,9 @@ def score_library(
     over = np.nonzero(status == _abi.LIG_OVERFLOW)[0]
     if len(over):
         sub = host_batch.select(over)
-        o2 = score_batch(model, DeviceLigandBatch.from_host(sub, model.device), weights, BIG_CONFIG, with_stats=with_stats)
+        o2 = score_batch(
+            model, DeviceLigandBatch.from_host(sub, model.device), weights, big_config(model), with_stats=with_stats
+        )
         scores[over] = o2["scores"].cpu().numpy()
         status[over] = o2["status"].cpu().numpy()
         if with_stats:
@@ -181,6 +200,8 @@ def topk(scores: torch.Tensor, k: int, id_base: int = 0, stream: torch.cuda.Stre
             C.c_void_p(s.cuda_stream),
         )  # fmt: skip
         _lib.check(rc, "pmnet_topk")
-        # ws must outlive the enqueued kernels
-        s.synchronize()
+        # `ws` goes back to torch's stream-ordered caching allocator when it is dropped: it cannot be handed to
+        # work on this stream before the kernels enqueued above have run. A foreign stream needs recording.
+        if stream is not None:
+            ws.record_stream(stream)
     return out_s, out_i

@@ -1,0 +1,246 @@
+"""Library screening driver: the data-parallel loop of the reference's `screening.py:46-75`
+(`Pool.map(model.scoring_file, files)` -> sort by score) on GPUs.
+
+* one process per GPU; the library is cut into blocks of `block_ligands` ligands and block b belongs to rank
+  b mod world (interleaving evens out the DFS-cost variance between regions of a library);
+* host-resident libraries stream through two device staging slots: the copy of block k+1 (pinned host -> HBM, on a
+  copy stream) overlaps the scoring kernel of block k;
+* every rank keeps the k best (score, ligand id) of its shard; the only collective is one all-gather of those
+  k pairs per rank, followed by the same merge on every rank (descending score, ties by ascending id - what
+  sorting the reference's full result list gives for its head).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _abi
+from .packing import LigandBatch, PackedModel
+from .scoring import DeviceLigandBatch, DeviceModel, ScoreConfig, big_config, score_batch, topk
+
+
+def shard_blocks(n_ligands: int, rank: int, world: int, block_ligands: int) -> list[tuple[int, int]]:
+    """[begin, end) ligand ranges owned by `rank`: block b -> rank b mod world."""
+    n_blocks = -(-n_ligands // block_ligands)
+    return [
+        (b * block_ligands, min(n_ligands, (b + 1) * block_ligands)) for b in range(rank, n_blocks, world)
+    ]
+
+
+def merge_topk(scores: torch.Tensor, ids: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """k best of candidate (score, id) pairs: descending score, ties by ascending id; padding ids (-1) last."""
+    valid = ids >= 0
+    s = torch.where(valid, scores, torch.full_like(scores, float("-inf")))
+    big = torch.iinfo(torch.int64).max
+    key_id = torch.where(valid, ids, torch.full_like(ids, big))
+    o1 = torch.sort(key_id, stable=True).indices
+    o2 = torch.sort(s[o1], descending=True, stable=True).indices
+    order = o1[o2][:k]
+    out_s, out_i = s[order], ids[order]
+    if out_s.numel() < k:
+        pad = k - out_s.numel()
+        out_s = torch.cat([out_s, torch.full((pad,), float("-inf"), dtype=s.dtype, device=s.device)])
+        out_i = torch.cat([out_i, torch.full((pad,), -1, dtype=ids.dtype, device=ids.device)])
+    return out_s, out_i
+
+
+def gather_topk(scores: torch.Tensor, ids: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """All-gather every rank's top-k and merge (identical result on every rank). No-op without a process group."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return merge_topk(scores, ids, k)
+    world = dist.get_world_size()
+    gs = torch.empty(world * k, dtype=scores.dtype, device=scores.device)
+    gi = torch.empty(world * k, dtype=ids.dtype, device=ids.device)
+    dist.all_gather_into_tensor(gs, scores.contiguous())
+    dist.all_gather_into_tensor(gi, ids.contiguous())
+    return merge_topk(gs, gi, k)
+
+
+def pin_library(lib: LigandBatch) -> LigandBatch:
+    """Copy a host library into page-locked memory (numpy views of pinned torch tensors) for async H2D."""
+    arrays = {}
+    keep = []
+    for k, v in lib.arrays().items():
+        t = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
+        keep.append(t)
+        arrays[k] = t.numpy()
+    out = LigandBatch.from_arrays(arrays)
+    out._pinned = keep  # keep the owning tensors alive
+    return out
+
+
+@dataclass
+class ScreenResult:
+    topk_scores: torch.Tensor  # [k] fp32, device, descending
+    topk_ids: torch.Tensor  # [k] int64 global ligand ids (-1 padding)
+    scores: np.ndarray | torch.Tensor | None  # this rank's scores in processing order
+    ids: np.ndarray | None  # global ligand id of each entry of `scores` (None = identity)
+    n_ligands: int
+    n_conformers: int
+    n_overflow: int
+    launches: int  # kernels of this package launched
+
+
+class _Slot:
+    """Device staging buffers for one in-flight block."""
+
+    def __init__(self, caps: dict[str, int], dtypes: dict[str, torch.dtype], device):
+        self.t = {k: torch.empty(max(1, caps[k]), dtype=dtypes[k], device=device) for k in caps}
+        self.ready = torch.cuda.Event()  # H2D finished
+        self.free = torch.cuda.Event()  # kernel finished, slot reusable
+
+
+class Screener:
+    def __init__(
+        self,
+        model,
+        device=None,
+        weights: dict[str, float] | None = None,
+        k: int = 1000,
+        config: ScoreConfig | None = None,
+        block_ligands: int = 65536,
+    ):
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        packed = model if isinstance(model, PackedModel) else model.packed
+        self.model = DeviceModel(packed, self.device)
+        self.weights = weights
+        self.k = int(k)
+        self.config = config or ScoreConfig()
+        self.block_ligands = int(block_ligands)
+        self._copy_stream = torch.cuda.Stream(self.device)
+        self._slots: list[_Slot] | None = None
+        self._slot_caps: dict[str, int] | None = None
+        # optional CUDA-event pairs around every scoring launch (bench.py: kernel duration for the roofline)
+        self.record_kernel_events = False
+        self.kernel_events: list[tuple[torch.cuda.Event, torch.cuda.Event]] = []
+
+    def _timed_score(self, batch, **kw):
+        if not self.record_kernel_events:
+            return score_batch(self.model, batch, self.weights, self.config, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = score_batch(self.model, batch, self.weights, self.config, **kw)
+        e1.record()
+        self.kernel_events.append((e0, e1))
+        return out
+
+    # ------------------------------------------------------------------ device-resident shard: one launch
+    def screen_device(self, batch: DeviceLigandBatch, id_base: int = 0, gather: bool = True) -> ScreenResult:
+        out = self._timed_score(batch)
+        n_over = 0
+        ks, ki = topk(out["scores"], self.k, id_base)
+        launches = 3  # scoring kernel + id fill + top-k write-out (the radix sort passes are CUB's)
+        if gather:
+            ks, ki = gather_topk(ks, ki, self.k)
+        return ScreenResult(ks, ki, out["scores"], None, batch.n_ligands, batch.n_conformers_total, n_over, launches)
+
+    # ------------------------------------------------------------------ host-resident library: streamed
+    def _block_slices(self, lib: LigandBatch, a: int, b: int):
+        n0, n1 = int(lib.lig_node_off[a]), int(lib.lig_node_off[b])
+        q0, q1 = int(lib.lig_cluster_off[a]), int(lib.lig_cluster_off[b])
+        c0, c1 = int(lib.cluster_node_off[q0]), int(lib.cluster_node_off[q1])
+        x0, x1 = int(lib.coord_off[a]), int(lib.coord_off[b])
+        sl = dict(
+            lig_node_off=lib.lig_node_off[a : b + 1],
+            lig_cluster_off=lib.lig_cluster_off[a : b + 1],
+            cluster_node_off=lib.cluster_node_off[q0 : q1 + 1],
+            cluster_nodes=lib.cluster_nodes[c0:c1],
+            node_type_mask=lib.node_type_mask[n0:n1],
+            n_conf=lib.n_conf[a:b],
+            coord_off=lib.coord_off[a : b + 1],
+            coords=lib.coords[x0:x1],
+        )
+        bases = dict(coord_base=x0, node_base=n0, cluster_base=q0, cnode_base=c0)
+        return sl, bases
+
+    def _ensure_slots(self, lib: LigandBatch, blocks):
+        caps = {k: 0 for k in _abi.BATCH_FIELDS}
+        for a, b in blocks:
+            sl, _ = self._block_slices(lib, a, b)
+            for k, v in sl.items():
+                caps[k] = max(caps[k], v.shape[0])
+        if self._slots is not None and all(self._slot_caps[k] >= caps[k] for k in caps):
+            return
+        dtypes = {k: torch.from_numpy(v[:0]).dtype for k, v in lib.arrays().items()}
+        self._slots = [_Slot(caps, dtypes, self.device) for _ in range(2)]
+        self._slot_caps = caps
+
+    def screen_host(
+        self, lib: LigandBatch, rank: int = 0, world: int = 1, gather: bool = True, return_scores: bool = True
+    ) -> ScreenResult:
+        """Score this rank's blocks of a host library (pinned memory makes the copies asynchronous)."""
+        dev = self.device
+        blocks = shard_blocks(lib.num_ligands, rank, world, self.block_ligands)
+        n_mine = sum(b - a for a, b in blocks)
+        scores = torch.empty(n_mine, dtype=torch.float32, device=dev)
+        status = torch.empty(n_mine, dtype=torch.int32, device=dev)
+        cand_s, cand_i = [], []
+        launches = 0
+        n_conf = 0
+        if blocks:
+            self._ensure_slots(lib, blocks)
+        compute = torch.cuda.current_stream(dev)
+        pos = 0
+        for it, (a, b) in enumerate(blocks):
+            slot = self._slots[it % 2]
+            sl, bases = self._block_slices(lib, a, b)
+            with torch.cuda.stream(self._copy_stream):
+                if it >= 2:
+                    self._copy_stream.wait_event(slot.free)
+                views = {}
+                for k, v in sl.items():
+                    dst = slot.t[k][: v.shape[0]]
+                    dst.copy_(torch.from_numpy(v), non_blocking=True)
+                    views[k] = dst
+                slot.ready.record(self._copy_stream)
+            compute.wait_event(slot.ready)
+            nb = b - a
+            nc = int(lib.n_conf[a:b].sum())
+            n_conf += nc
+            db = DeviceLigandBatch(views, nb, nc, bases)
+            self._timed_score(db, out_scores=scores[pos : pos + nb], out_status=status[pos : pos + nb])
+            slot.free.record(compute)
+            ks, ki = topk(scores[pos : pos + nb], self.k, a)
+            cand_s.append(ks)
+            cand_i.append(ki)
+            launches += 3
+            pos += nb
+        ids = np.concatenate([np.arange(a, b, dtype=np.int64) for a, b in blocks]) if blocks else np.zeros(0, np.int64)
+        # ligands whose pair table overflowed the per-warp scratch: re-run them with the roomy configuration
+        st = status.cpu().numpy()
+        over = np.nonzero(st == _abi.LIG_OVERFLOW)[0]
+        if len(over):
+            sub = lib.select(ids[over])
+            o2 = score_batch(self.model, DeviceLigandBatch.from_host(sub, dev), self.weights, big_config(self.model))
+            scores[torch.from_numpy(over).to(dev)] = o2["scores"]
+            launches += 1
+            over_ids = torch.from_numpy(ids[over]).to(dev)
+            # drop the placeholder entries of these ligands from the per-block candidates
+            cand_i = [torch.where(torch.isin(ci, over_ids), torch.full_like(ci, -1), ci) for ci in cand_i]
+            cand_s.append(o2["scores"])
+            cand_i.append(over_ids)
+        if cand_s:
+            ks, ki = merge_topk(torch.cat(cand_s), torch.cat(cand_i), self.k)
+        else:
+            ks = torch.full((self.k,), float("-inf"), dtype=torch.float32, device=dev)
+            ki = torch.full((self.k,), -1, dtype=torch.int64, device=dev)
+        if gather:
+            ks, ki = gather_topk(ks, ki, self.k)
+        host_scores = scores.cpu().numpy() if return_scores else None
+        return ScreenResult(ks, ki, host_scores, ids, n_mine, n_conf, int(len(over)), launches)
+
+
+def write_csv(path: str, names, scores) -> None:
+    """The reference's output format (screening.py:70-75): `path,score`, descending by score."""
+    order = np.lexsort((np.arange(len(scores)), -np.asarray(scores, dtype=np.float64)))
+    with open(path, "w") as w:
+        w.write("path,score\n")
+        for i in order:
+            w.write(f"{names[i]},{float(scores[i])}\n")

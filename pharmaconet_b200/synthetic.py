@@ -260,3 +260,117 @@ def make_hotspot_infos(
             )
         )
     return infos
+
+
+def make_library_device(
+    n_ligands: int,
+    num_conformers: int,
+    seed: int,
+    device="cuda",
+    n_templates: int = 4096,
+    flex: float = 0.45,
+    noise: float = 0.08,
+):
+    """Large synthetic library built on the GPU (benchmarks): `n_templates` topologies from `make_template`, each
+    replicated with independently drawn coordinates (same recipe as `make_conformers`, in torch on `device`).
+    Ligand i uses template i % n_templates, so any prefix of the library is a representative sample.
+    Returns a `scoring.DeviceLigandBatch`. Data creation only - nothing here is scored or timed."""
+    import torch
+
+    from .ligand import build_topology
+    from .scoring import DeviceLigandBatch
+
+    dev = torch.device(device)
+    rng = np.random.default_rng(seed)
+    T = max(1, min(n_templates, n_ligands))
+    C = int(num_conformers)
+    stride = (C + 3) // 4 * 4
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+
+    templates, tops = [], []
+    for _ in range(T):
+        t = make_template(rng)
+        while len(t.pharmacophores) == 0:
+            t = make_template(rng)
+        templates.append(t)
+        tops.append(build_topology(t.typed()))
+    ordered = [top.ordered_cluster_nodes() for top in tops]
+    tid = np.arange(n_ligands, dtype=np.int64) % T
+
+    def offsets(per_ligand: np.ndarray) -> np.ndarray:
+        off = np.zeros(len(per_ligand) + 1, dtype=np.int64)
+        np.cumsum(per_ligand, out=off[1:])
+        return off
+
+    nn_t = np.asarray([top.num_nodes for top in tops], dtype=np.int64)
+    ncl_t = np.asarray([len(o) for o in ordered], dtype=np.int64)
+    ncn_t = np.asarray([sum(len(c) for c in o) for o in ordered], dtype=np.int64)
+    node_off = offsets(nn_t[tid])
+    clu_off = offsets(ncl_t[tid])
+    cn_lig_off = offsets(ncn_t[tid])  # first cluster-node of each ligand
+    coord_off = offsets(nn_t[tid] * 3 * stride)
+    assert node_off[-1] < 2**31 and cn_lig_off[-1] < 2**31
+
+    masks = np.empty(int(node_off[-1]), dtype=np.uint8)
+    cl_nodes = np.empty(int(cn_lig_off[-1]), dtype=np.uint8)
+    cn_off = np.empty(int(clu_off[-1]) + 1, dtype=np.int64)
+    cn_off[-1] = cn_lig_off[-1]
+    coords = torch.empty(int(coord_off[-1]), dtype=torch.float32, device=dev)
+    for t_i, (t, top) in enumerate(zip(templates, tops)):
+        ligs = np.arange(t_i, n_ligands, T)
+        r = len(ligs)
+        if r == 0:
+            continue
+        nn = int(nn_t[t_i])
+        masks[(node_off[ligs][:, None] + np.arange(nn)[None, :]).reshape(-1)] = np.tile(top.node_type_mask, r)
+        flat = np.asarray([n for c in ordered[t_i] for n in c], dtype=np.uint8)
+        cl_nodes[(cn_lig_off[ligs][:, None] + np.arange(len(flat))[None, :]).reshape(-1)] = np.tile(flat, r)
+        starts = np.concatenate([[0], np.cumsum([len(c) for c in ordered[t_i]])[:-1]]).astype(np.int64)
+        cn_off[(clu_off[ligs][:, None] + np.arange(len(starts))[None, :]).reshape(-1)] = (
+            cn_lig_off[ligs][:, None] + starts[None, :]
+        ).reshape(-1)
+        # ---- coordinates on the device: [r, Nn, 3, stride]
+        F, N = t.n_frag, len(t.atomic_nums)
+        f = torch.as_tensor(t.frag_of_atom, device=dev)
+        steps = torch.randn((r, F, 3), generator=gen, device=dev, dtype=torch.float32)
+        steps = steps / steps.norm(dim=-1, keepdim=True) * (2.5 + 1.5 * torch.rand((r, F, 1), generator=gen, device=dev))
+        steps[:, 0] = 0.0
+        centres = steps.cumsum(dim=1)
+        q = torch.randn((r, F, 4), generator=gen, device=dev, dtype=torch.float32)
+        q = q / q.norm(dim=-1, keepdim=True)
+        w, x, y, z = q.unbind(-1)
+        rot = torch.stack(
+            [
+                1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y),
+            ],
+            dim=-1,
+        ).reshape(r, F, 3, 3)  # fmt: skip
+        bend = (flex * torch.randn((r, C, F, 3), generator=gen, device=dev, dtype=torch.float32)).cumsum(dim=2)
+        bend[:, :, 0] = 0.0
+        local = torch.einsum("rnij,nj->rni", rot[:, f], torch.as_tensor(t.local_xyz, device=dev))
+        pos = centres[:, f][:, :, None, :] + bend[:, :, f, :].permute(0, 2, 1, 3) + local[:, :, None, :]
+        pos = pos + noise * torch.randn(pos.shape, generator=gen, device=dev, dtype=torch.float32)  # [r, N, C, 3]
+        A = torch.zeros((nn, N), dtype=torch.float32, device=dev)
+        for n_i, ctr in enumerate(top.node_center_atoms):
+            A[n_i, list(ctr)] = 1.0 / len(ctr)
+        npos = torch.einsum("na,racx->rnxc", A, pos)  # [r, Nn, 3, C]
+        if stride != C:
+            npos = torch.nn.functional.pad(npos, (0, stride - C))
+        row = nn * 3 * stride
+        dst = torch.as_tensor(coord_off[ligs], device=dev)[:, None] + torch.arange(row, device=dev)[None, :]
+        coords[dst.reshape(-1)] = npos.reshape(-1)
+    host = dict(
+        lig_node_off=node_off.astype(np.int32),
+        lig_cluster_off=clu_off.astype(np.int32),
+        cluster_node_off=cn_off.astype(np.int32),
+        cluster_nodes=cl_nodes,
+        node_type_mask=masks,
+        n_conf=np.full(n_ligands, C, dtype=np.int32),
+        coord_off=coord_off,
+    )
+    tensors = {k: torch.from_numpy(v).to(dev) for k, v in host.items()}
+    tensors["coords"] = coords
+    return DeviceLigandBatch(tensors, n_ligands, n_ligands * C)
