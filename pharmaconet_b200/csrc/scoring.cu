@@ -35,7 +35,6 @@ constexpr int kMaxDepth = PMNET_MAX_DEPTH;      // levels
 constexpr int kSlots = kMaxDepth + 1;           // depths 0..20 (root = depth 0)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxClusterNodes = 32;            // model nodes per model cluster handled by the match stream
-constexpr int kNmBytesPerEntry = 64;            // match-stream budget per entry (average)
 
 thread_local char g_err[256] = "";
 
@@ -52,9 +51,11 @@ struct WarpLayout {
   int t_cap;        // max entries (level, model cluster) per ligand
   int pair_cap;     // max pair entries
   int rows;         // pair-score rows (128 B each)
-  size_t off_rows, off_v, off_prow, off_masks, off_rowbase, off_srow, off_nmoff, off_geo, off_entmc, off_entlev,
-      off_nmcnt, off_nm;
-  size_t nm_cap;
+  int dn_cap;       // max ligand nodes in the selected levels (distance table is dn_cap x dn_cap rows)
+  int rec_cap;      // max node-match records
+  size_t off_rows, off_dist, off_v, off_prow, off_masks, off_rowbase, off_srow, off_nmoff, off_geo, off_rec,
+      off_entmc, off_entlev, off_nmcnt, off_lnode, off_mlist;
+  size_t mlist_cap;
   size_t bytes;     // per warp, multiple of 256
 };
 
@@ -65,8 +66,12 @@ __host__ __device__ inline WarpLayout make_layout(int n_model_clusters, int scra
   L.t_cap = (t + 31) / 32 * 32;
   L.rows = scratch_rows;
   L.pair_cap = scratch_rows * 4;
+  // distance table: 64 nodes by default (8192 rows); the roomy re-run configuration (>= 65536 rows) takes 255
+  L.dn_cap = scratch_rows >= 65536 ? 255 : (scratch_rows >= 4096 ? 64 : 32);
+  L.rec_cap = L.t_cap * 8;
   size_t o = 0;
   L.off_rows = o;    o += (size_t)L.rows * 128;
+  L.off_dist = o;    o += (size_t)L.dn_cap * L.dn_cap * 128;
   L.off_v = o;       o += (size_t)L.pair_cap * 4;
   L.off_prow = o;    o += (size_t)L.pair_cap * 4;
   L.off_masks = o;   o += (size_t)kSlots * L.t_cap * 4;
@@ -74,10 +79,12 @@ __host__ __device__ inline WarpLayout make_layout(int n_model_clusters, int scra
   L.off_srow = o;    o += (size_t)L.t_cap * 4;
   L.off_nmoff = o;   o += (size_t)L.t_cap * 4;
   L.off_geo = o;     o += (size_t)kMaxDepth * 4 * 32 * 4;
+  L.off_rec = o;     o += (size_t)L.rec_cap * 4;
   L.off_entmc = o;   o += (size_t)L.t_cap;
   L.off_entlev = o;  o += (size_t)L.t_cap;
   L.off_nmcnt = o;   o += (size_t)L.t_cap;
-  L.off_nm = o;      L.nm_cap = (size_t)L.t_cap * kNmBytesPerEntry; o += L.nm_cap;
+  L.off_lnode = o;   o += 256;
+  L.off_mlist = o;   L.mlist_cap = 65536; o += L.mlist_cap;
   L.bytes = align_up(o, 256);
   return L;
 }
@@ -87,7 +94,7 @@ constexpr size_t kHeaderBytes = 256;
 // ---------------------------------------------------------------- shared-memory model image
 struct SmemModel {
   int nm, km;
-  float4* edge;           // [nm*nm] {mu, r = 1/sigma, wr = w[type b] * r, 0}
+  float4* edge;           // [nm*nm] {mu, r = 1/sigma, wr = w[type b] * r, w[type a] * wr}
   float* cdist;           // [km*km]
   float* csize;           // [km*km]
   float* wnode;           // [nm] weight of each model node's type
@@ -113,6 +120,7 @@ struct WarpSmem {
   float tot[kSlots][32];      // per-depth conformer totals
   int lev_start[kMaxDepth + 1];
   int lev_q[kMaxDepth];       // ligand cluster (global CSR index) of each level
+  int lev_nbase[kMaxDepth];   // first local node id of each level
   int pad[3];
 };
 
@@ -141,31 +149,53 @@ __device__ __forceinline__ float norm3(float dx, float dy, float dz) {
   return __fsqrt_rn(s);
 }
 
+// exp(-0.5 * s2) on the SFU: ex2.approx(s2 * (-0.5 * log2 e)); relative error ~2^-22 + |x| 2^-24
+__device__ __forceinline__ float gauss(float s2) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s2 * -0.72134752044448170368f));
+  return r;
+}
+
+// Node-match record (one per ligand node of an entry with >= 1 matched model node, graph_match.py:139-172):
+//   bits 0-7 local ligand node id, 8-15 M = number of matched model nodes,
+//   16-31: the model node itself when M == 1, else the offset of the M model-node bytes in `mlist`.
+__device__ __forceinline__ int rec_node(uint32_t r) { return r & 255u; }
+__device__ __forceinline__ int rec_m(uint32_t r) { return (r >> 8) & 255u; }
+__device__ __forceinline__ int rec_x(uint32_t r) { return r >> 16; }
+
 // One ligand-node pair against two matched model-node lists (match_utils_numba.py:67-86): returns the fp32
 // likelihood / (M*N) and whether this conformer fails the "half of the pairs within 2 sigma" test.
-__device__ __forceinline__ float pair_term(const SmemModel& sm, float d, const uint8_t* __restrict__ m1, int M,
-                                           const uint8_t* __restrict__ m2, int N, bool& fails) {
+__device__ __forceinline__ float pair_term(const SmemModel& sm, const uint8_t* __restrict__ mlist, float d,
+                                           uint32_t r1, uint32_t r2, bool& fails) {
+  const int M = rec_m(r1), N = rec_m(r2);
+  if (M == 1 && N == 1) {
+    const float4 e = sm.edge[rec_x(r1) * sm.nm + rec_x(r2)];
+    const float s = __fmul_rn(__fsub_rn(d, e.x), e.y);
+    const float s2 = __fmul_rn(s, s);
+    fails = !(s2 < 4.0f);
+    return e.w * gauss(s2);
+  }
+  const int x1 = rec_x(r1), x2 = rec_x(r2);
   int npass = 0;
   float lik = 0.0f;
   for (int a = 0; a < M; ++a) {
-    const int ma = m1[a];
+    const int ma = (M == 1) ? x1 : (int)mlist[x1 + a];
     const float4* row = sm.edge + ma * sm.nm;
-    float l = 0.0f;
     for (int b = 0; b < N; ++b) {
-      const float4 e = row[m2[b]];
+      const int mb = (N == 1) ? x2 : (int)mlist[x2 + b];
+      const float4 e = row[mb];
       const float s = __fmul_rn(__fsub_rn(d, e.x), e.y);
       const float s2 = __fmul_rn(s, s);
-      l = fmaf(e.z, expf(-0.5f * s2), l);
+      lik = fmaf(e.w, gauss(s2), lik);
       npass += (s2 < 4.0f) ? 1 : 0;
     }
-    lik = fmaf(sm.wnode[ma], l, lik);
   }
   const int mn = M * N;
   fails = npass < ((mn + 1) >> 1);
   return lik * __frcp_rn((float)mn);
 }
 
-__global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args) {
+__global__ void __launch_bounds__(256, 2) pmnet_score_kernel(const KernelArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
@@ -192,10 +222,10 @@ __global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args)
   WarpSmem& ws = ws_all[warp_in_block];
 
   for (int i = threadIdx.x; i < NM * NM; i += blockDim.x) {
-    const int b = i % NM;
+    const int a = i / NM, b = i % NM;
     const float r = __fdiv_rn(1.0f, gm.edge_sigma[i]);
     const float wr = __fmul_rn(args.w[gm.node_type[b]], r);
-    sm.edge[i] = make_float4(gm.edge_mu[i], r, wr, 0.0f);
+    sm.edge[i] = make_float4(gm.edge_mu[i], r, wr, __fmul_rn(args.w[gm.node_type[a]], wr));
   }
   for (int i = threadIdx.x; i < KM * KM; i += blockDim.x) {
     sm.cdist[i] = gm.cluster_dist[i];
@@ -222,10 +252,13 @@ __global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args)
   int32_t* const srow = (int32_t*)(wbase + LY.off_srow);
   uint32_t* const nmoff = (uint32_t*)(wbase + LY.off_nmoff);
   float* const geo = (float*)(wbase + LY.off_geo);
+  float* const dist = (float*)(wbase + LY.off_dist);
+  uint32_t* const rec = (uint32_t*)(wbase + LY.off_rec);
   uint8_t* const entmc = wbase + LY.off_entmc;
   uint8_t* const entlev = wbase + LY.off_entlev;
   uint8_t* const nmcnt = wbase + LY.off_nmcnt;
-  uint8_t* const nms = wbase + LY.off_nm;
+  uint8_t* const lnode = wbase + LY.off_lnode;
+  uint8_t* const mlist = wbase + LY.off_mlist;
   unsigned int* const counter = (unsigned int*)args.workspace;
 
   const PmLigandBatch& B = args.batch;
@@ -253,9 +286,8 @@ __global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args)
       const bool on = lane < C;
       const unsigned cmask_full = (C == 32) ? kFull : ((1u << C) - 1u);
 
-      // ================= phase 0: levels, entries, node-match streams (graph_match.py:85-92, 124-172)
-      int L = 0, T = 0;
-      uint32_t nm_used = 0;
+      // ================= phase 0: levels, entries, node-match records (graph_match.py:85-92, 124-172)
+      int L = 0, T = 0, NL = 0;
       bool overflow = false;
       for (int q = q0; q < q1 && L < kMaxDepth && !overflow; ++q) {
         const int c0 = B.cluster_node_off[q], c1 = B.cluster_node_off[q + 1];
@@ -280,12 +312,19 @@ __global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args)
         }
         if (overflow) break;
         if (T > t_level) {
+          const int n = c1 - c0;
+          if (NL + n > LY.dn_cap) {
+            overflow = true;
+            break;
+          }
           if (lane == 0) {
             ws.lev_start[L] = t_level;
             ws.lev_q[L] = q;
+            ws.lev_nbase[L] = NL;
           }
+          // the level's nodes get consecutive local ids (cluster order, ligand.py:387-395)
+          for (int i = lane; i < n; i += 32) lnode[NL + i] = cl_nodes[c0 + i];
           // cluster centre and size per conformer (ligand.py:458-473), fp32 sequential like numpy
-          const int n = c1 - c0;
           float cx = 0.f, cy = 0.f, cz = 0.f;
           for (int i = c0; i < c1; ++i) {
             const int node = cl_nodes[i];
@@ -309,6 +348,7 @@ __global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args)
           }
           float* g = geo + (size_t)L * 128;
           g[lane] = cx; g[32 + lane] = cy; g[64 + lane] = cz; g[96 + lane] = sz;
+          NL += n;
           ++L;
         }
       }
@@ -316,59 +356,70 @@ __global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args)
       if (!overflow && L > 0) {
         if (lane == 0) ws.lev_start[L] = T;
         __syncwarp();
-        // node-match streams: per entry a list of [ligand node, M, m_0..m_{M-1}] (graph_match.py:139-172)
+        // node-match records, one lane per entry: count, exclusive scan for the offsets, then fill
+        uint32_t rec_used = 0, ml_used = 0;
         for (int e0 = 0; e0 < T && !overflow; e0 += 32) {
           const int e = e0 + lane;
-          // each lane builds the stream of one entry; sizes first, then an exclusive scan for the offsets
-          uint32_t bytes = 0;
-          int cnt = 0;
+          uint32_t nrec = 0, nml = 0;
           bool toobig = false;
-          int q = 0, k = 0;
+          int q = 0, k = 0, nb = 0;
           if (e < T) {
-            q = ws.lev_q[entlev[e]];
+            const int lev = entlev[e];
+            q = ws.lev_q[lev];
+            nb = ws.lev_nbase[lev];
             k = entmc[e];
             for (int i = B.cluster_node_off[q]; i < B.cluster_node_off[q + 1]; ++i) {
               const unsigned tm = tmask[cl_nodes[i]];
               int M = 0;
               for (int j = sm.cnode_off[k]; j < sm.cnode_off[k + 1]; ++j) M += (tm >> sm.ntype[sm.cnodes[j]]) & 1u;
               if (M > kMaxClusterNodes) toobig = true;
-              if (M > 0) {
-                bytes += 2 + M;
-                ++cnt;
-              }
+              if (M > 0) ++nrec;
+              if (M > 1) nml += M;
             }
-            if (cnt > 255) toobig = true;
+            if (nrec > 255) toobig = true;
           }
-          uint32_t incl = bytes;
+          uint32_t irec = nrec, iml = nml;
           for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(kFull, incl, o);
-            if (lane >= o) incl += v;
+            const uint32_t v1 = __shfl_up_sync(kFull, irec, o), v2 = __shfl_up_sync(kFull, iml, o);
+            if (lane >= o) {
+              irec += v1;
+              iml += v2;
+            }
           }
-          const uint32_t total = __shfl_sync(kFull, incl, 31);
-          if (__any_sync(kFull, toobig) || nm_used + total > LY.nm_cap) {
+          const uint32_t trec = __shfl_sync(kFull, irec, 31), tml = __shfl_sync(kFull, iml, 31);
+          if (__any_sync(kFull, toobig) || rec_used + trec > (uint32_t)LY.rec_cap || ml_used + tml > LY.mlist_cap) {
             overflow = true;
             break;
           }
           if (e < T) {
-            uint32_t o = nm_used + incl - bytes;
-            nmoff[e] = o;
-            nmcnt[e] = (uint8_t)cnt;
-            for (int i = B.cluster_node_off[q]; i < B.cluster_node_off[q + 1]; ++i) {
-              const int node = cl_nodes[i];
-              const unsigned tm = tmask[node];
-              int M = 0;
+            uint32_t ro = rec_used + irec - nrec, mo = ml_used + iml - nml;
+            nmoff[e] = ro;
+            nmcnt[e] = (uint8_t)nrec;
+            const int c0 = B.cluster_node_off[q], c1 = B.cluster_node_off[q + 1];
+            for (int i = c0; i < c1; ++i) {
+              const unsigned tm = tmask[cl_nodes[i]];
+              int M = 0, first = 0;
               for (int j = sm.cnode_off[k]; j < sm.cnode_off[k + 1]; ++j) {
                 const int mn = sm.cnodes[j];
-                if ((tm >> sm.ntype[mn]) & 1u) nms[o + 2 + M++] = (uint8_t)mn;
+                if ((tm >> sm.ntype[mn]) & 1u) {
+                  if (M == 0) first = mn;
+                  ++M;
+                }
               }
-              if (M > 0) {
-                nms[o] = (uint8_t)node;
-                nms[o + 1] = (uint8_t)M;
-                o += 2 + M;
+              if (M == 0) continue;
+              uint32_t x = (uint32_t)first;
+              if (M > 1) {
+                x = mo;
+                for (int j = sm.cnode_off[k]; j < sm.cnode_off[k + 1]; ++j) {
+                  const int mn = sm.cnodes[j];
+                  if ((tm >> sm.ntype[mn]) & 1u) mlist[mo++] = (uint8_t)mn;
+                }
               }
+              rec[ro++] = (uint32_t)(nb + (i - c0)) | ((uint32_t)M << 8) | (x << 16);
             }
           }
-          nm_used += total;
+          rec_used += trec;
+          ml_used += tml;
         }
         // pair-index base of each entry: V/prow rows of e1 cover all entries of later levels
         if (!overflow) {
@@ -381,6 +432,21 @@ __global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args)
           }
           st_pairs = (uint32_t)run;
           if (run > LY.pair_cap) overflow = true;
+        }
+        // ligand node-pair distances (LigandEdge.set_distances, ligand.py:349-351), upper triangle of NL x NL
+        if (!overflow) {
+          for (int i = 0; i < NL - 1; ++i) {
+            const int ni = lnode[i];
+            const float xi = ld_coord(xyz, stride, ni, 0, lane, on), yi = ld_coord(xyz, stride, ni, 1, lane, on),
+                        zi = ld_coord(xyz, stride, ni, 2, lane, on);
+            float* drow = dist + ((size_t)i * NL) * 32 + lane;
+            for (int j = i + 1; j < NL; ++j) {
+              const int nj = lnode[j];
+              drow[(size_t)j * 32] = norm3(__fsub_rn(xi, ld_coord(xyz, stride, nj, 0, lane, on)),
+                                          __fsub_rn(yi, ld_coord(xyz, stride, nj, 1, lane, on)),
+                                          __fsub_rn(zi, ld_coord(xyz, stride, nj, 2, lane, on)));
+            }
+          }
         }
         __syncwarp();
       }
@@ -397,22 +463,15 @@ __global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args)
           int r = -1;
           if (cnt >= 2) {
             float sc = 0.0f;
-            uint32_t o1 = nmoff[e];
-            for (int i = 0; i < cnt; ++i) {
-              const int n1 = nms[o1], M = nms[o1 + 1];
-              const float x1 = ld_coord(xyz, stride, n1, 0, lane, on), y1 = ld_coord(xyz, stride, n1, 1, lane, on),
-                          z1 = ld_coord(xyz, stride, n1, 2, lane, on);
-              uint32_t o2 = o1 + 2 + M;
+            const uint32_t off = nmoff[e];
+            for (int i = 0; i < cnt - 1; ++i) {
+              const uint32_t r1 = rec[off + i];
+              const float* drow = dist + ((size_t)rec_node(r1) * NL) * 32 + lane;
               for (int j = i + 1; j < cnt; ++j) {
-                const int n2 = nms[o2], N = nms[o2 + 1];
-                const float d = norm3(__fsub_rn(x1, ld_coord(xyz, stride, n2, 0, lane, on)),
-                                      __fsub_rn(y1, ld_coord(xyz, stride, n2, 1, lane, on)),
-                                      __fsub_rn(z1, ld_coord(xyz, stride, n2, 2, lane, on)));
+                const uint32_t r2 = rec[off + j];
                 bool f;
-                sc += pair_term(sm, d, nms + o1 + 2, M, nms + o2 + 2, N, f);
-                o2 += 2 + N;
+                sc += pair_term(sm, mlist, drow[(size_t)rec_node(r2) * 32], r1, r2, f);
               }
-              o1 += 2 + M;
             }
             if (nrows >= LY.rows) {
               overflow = true;
@@ -437,41 +496,37 @@ __global__ void __launch_bounds__(256) pmnet_score_kernel(const KernelArgs args)
               const int cnt1 = nmcnt[e1];
               const uint32_t off1 = nmoff[e1];
               const int pb = rowbase[e1];
+              const float* cd = sm.cdist + k * KM;
+              const float* cs = sm.csize + k * KM;
               for (int e2 = s2; e2 < e2_end; ++e2) {
                 const int l = entmc[e2];
                 // cluster prefilter (graph_match.py:263-268): min_c(|d_lig - d_mod| - size_lig) > size_mod
-                const float v = __fsub_rn(fabsf(__fsub_rn(ldist, sm.cdist[k * KM + l])), lsize);
-                const bool far = !on || (v > sm.csize[k * KM + l]);
+                const float v = __fsub_rn(fabsf(__fsub_rn(ldist, cd[l])), lsize);
+                const bool far = !on || (v > cs[l]);
                 unsigned valid = 0;
                 int r = -1;
                 if (!__all_sync(kFull, far)) {
                   const int cnt2 = nmcnt[e2];
+                  const uint32_t off2 = nmoff[e2];
                   const int thr2 = cnt1 * cnt2;  // fail <= 0.5*cnt1*cnt2  <=>  2*fail <= cnt1*cnt2
                   float sc = 0.0f;
                   int nfail = 0;
                   bool dead = false;
-                  uint32_t o1 = off1;
-                  for (int a = 0; a < cnt1 && !dead; ++a) {
-                    const int n1 = nms[o1], M = nms[o1 + 1];
-                    const float x1 = ld_coord(xyz, stride, n1, 0, lane, on), y1 = ld_coord(xyz, stride, n1, 1, lane, on),
-                                z1 = ld_coord(xyz, stride, n1, 2, lane, on);
-                    uint32_t o2 = nmoff[e2];
+                  for (int a = 0; a < cnt1; ++a) {
+                    const uint32_t r1 = rec[off1 + a];
+                    const float* drow = dist + ((size_t)rec_node(r1) * NL) * 32 + lane;
                     for (int b = 0; b < cnt2; ++b) {
-                      const int n2 = nms[o2], N = nms[o2 + 1];
-                      const float d = norm3(__fsub_rn(x1, ld_coord(xyz, stride, n2, 0, lane, on)),
-                                            __fsub_rn(y1, ld_coord(xyz, stride, n2, 1, lane, on)),
-                                            __fsub_rn(z1, ld_coord(xyz, stride, n2, 2, lane, on)));
+                      const uint32_t r2 = rec[off2 + b];
                       bool f;
-                      sc += pair_term(sm, d, nms + o1 + 2, M, nms + o2 + 2, N, f);
+                      sc += pair_term(sm, mlist, drow[(size_t)rec_node(r2) * 32], r1, r2, f);
                       nfail += f ? 1 : 0;
-                      // early exit when every conformer already failed (match_utils_numba.py:191-192)
-                      if (__all_sync(kFull, !on || (2 * nfail > thr2))) {
-                        dead = true;
-                        break;
-                      }
-                      o2 += 2 + N;
                     }
-                    o1 += 2 + M;
+                    // every conformer already failed: the pair is invalid whatever follows
+                    // (match_utils_numba.py:191-192 tests this after every term; the outcome is the same)
+                    if (__all_sync(kFull, !on || (2 * nfail > thr2))) {
+                      dead = true;
+                      break;
+                    }
                   }
                   if (!dead) valid = __ballot_sync(kFull, on && (2 * nfail <= thr2) && (sc > 0.0f));
                   if (valid) {

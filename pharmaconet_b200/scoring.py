@@ -93,7 +93,7 @@ def big_config(model) -> ScoreConfig:
     """A roomy configuration for ligands whose pair table overflowed the default per-warp scratch: rows for the
     worst case of this model (T = min(20 Km, 1024) entries, T^2/2 pairs), on fewer warps."""
     t = min(20 * model.num_clusters, 1024)
-    rows = max(8192, t * t // 2 + t)
+    rows = max(65536, t * t // 2 + t)  # >= 65536 rows also selects the 255-node distance table
     return ScoreConfig(warps_per_block=4, blocks=32, scratch_rows=rows)
 
 
