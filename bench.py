@@ -351,7 +351,9 @@ def main():
             "e2e": e2e, "gpu_launches": launches,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (prof or {}).get("dram_bytes_per_launch"),
+                # ncu --set full capture of the same kernel on 131072 ligands of this workload, scaled per ligand
+                "traffic": (prof["dram_bytes_per_ligand"] * n_lig) if prof else None,
+                "traffic_source": (prof or {}).get("source"),
                 "kernel": "pmnet_score_kernel", "kernel_ms_avg": kernel_ms_avg,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "note": "the path is instruction-issue bound, not HBM bound (DESIGN.md section 5): the HBM fraction "

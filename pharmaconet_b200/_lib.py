@@ -12,7 +12,7 @@ from . import _abi
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-SO_PATH = os.path.join(_PKG, "libpmnet_b200.so")
+SO_PATH = os.environ.get("PMNET_B200_SO") or os.path.join(_PKG, "libpmnet_b200.so")  # env override: developer A/B builds
 SOURCES = [os.path.join(_PKG, "csrc", "scoring.cu")]
 HEADERS = [os.path.join(_ROOT, "include", "pmnet_b200.h")]
 NVCC_FLAGS = [

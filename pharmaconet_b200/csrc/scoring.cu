@@ -79,7 +79,7 @@ __host__ __device__ inline WarpLayout make_layout(int n_model_clusters, int scra
   L.off_srow = o;    o += (size_t)L.t_cap * 4;
   L.off_nmoff = o;   o += (size_t)L.t_cap * 4;
   L.off_geo = o;     o += (size_t)kMaxDepth * 4 * 32 * 4;
-  L.off_rec = o;     o += (size_t)L.rec_cap * 4;
+  L.off_rec = o;     o += (size_t)L.rec_cap * 8;
   L.off_entmc = o;   o += (size_t)L.t_cap;
   L.off_entlev = o;  o += (size_t)L.t_cap;
   L.off_nmcnt = o;   o += (size_t)L.t_cap;
@@ -156,34 +156,33 @@ __device__ __forceinline__ float gauss(float s2) {
   return r;
 }
 
-// Node-match record (one per ligand node of an entry with >= 1 matched model node, graph_match.py:139-172):
-//   bits 0-7 local ligand node id, 8-15 M = number of matched model nodes,
-//   16-31: the model node itself when M == 1, else the offset of the M model-node bytes in `mlist`.
-__device__ __forceinline__ int rec_node(uint32_t r) { return r & 255u; }
-__device__ __forceinline__ int rec_m(uint32_t r) { return (r >> 8) & 255u; }
-__device__ __forceinline__ int rec_x(uint32_t r) { return r >> 16; }
+// Node-match record, 8 bytes (one per ligand node of an entry with >= 1 matched model node, graph_match.py:139-172):
+//   .x bits 0-7 local ligand node id, 8-15 M = number of matched model nodes, 16-31 offset of the model-node bytes
+//      in `mlist` when M > 4;  .y = the first four matched model nodes, one byte each (all of them when M <= 4).
+__device__ __forceinline__ int rec_node(uint2 r) { return r.x & 255u; }
+__device__ __forceinline__ int rec_m(uint2 r) { return (r.x >> 8) & 255u; }
+__device__ __forceinline__ int rec_model_node(uint2 r, int a, const uint8_t* __restrict__ mlist) {
+  return (a < 4) ? (int)((r.y >> (8 * a)) & 255u) : (int)mlist[(r.x >> 16) + a];
+}
 
 // One ligand-node pair against two matched model-node lists (match_utils_numba.py:67-86): returns the fp32
 // likelihood / (M*N) and whether this conformer fails the "half of the pairs within 2 sigma" test.
 __device__ __forceinline__ float pair_term(const SmemModel& sm, const uint8_t* __restrict__ mlist, float d,
-                                           uint32_t r1, uint32_t r2, bool& fails) {
+                                           uint2 r1, uint2 r2, bool& fails) {
   const int M = rec_m(r1), N = rec_m(r2);
   if (M == 1 && N == 1) {
-    const float4 e = sm.edge[rec_x(r1) * sm.nm + rec_x(r2)];
+    const float4 e = sm.edge[(r1.y & 255u) * sm.nm + (r2.y & 255u)];
     const float s = __fmul_rn(__fsub_rn(d, e.x), e.y);
     const float s2 = __fmul_rn(s, s);
     fails = !(s2 < 4.0f);
     return e.w * gauss(s2);
   }
-  const int x1 = rec_x(r1), x2 = rec_x(r2);
   int npass = 0;
   float lik = 0.0f;
   for (int a = 0; a < M; ++a) {
-    const int ma = (M == 1) ? x1 : (int)mlist[x1 + a];
-    const float4* row = sm.edge + ma * sm.nm;
+    const float4* row = sm.edge + rec_model_node(r1, a, mlist) * sm.nm;
     for (int b = 0; b < N; ++b) {
-      const int mb = (N == 1) ? x2 : (int)mlist[x2 + b];
-      const float4 e = row[mb];
+      const float4 e = row[rec_model_node(r2, b, mlist)];
       const float s = __fmul_rn(__fsub_rn(d, e.x), e.y);
       const float s2 = __fmul_rn(s, s);
       lik = fmaf(e.w, gauss(s2), lik);
@@ -192,10 +191,18 @@ __device__ __forceinline__ float pair_term(const SmemModel& sm, const uint8_t* _
   }
   const int mn = M * N;
   fails = npass < ((mn + 1) >> 1);
-  return lik * __frcp_rn((float)mn);
+  float inv;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"((float)mn));
+  return lik * inv;
 }
 
-__global__ void __launch_bounds__(256, 2) pmnet_score_kernel(const KernelArgs args) {
+#ifndef PM_BLOCK_THREADS
+#define PM_BLOCK_THREADS 256
+#endif
+#ifndef PM_MIN_BLOCKS
+#define PM_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_kernel(const KernelArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(256, 2) pmnet_score_kernel(const KernelArgs ar
   uint32_t* const nmoff = (uint32_t*)(wbase + LY.off_nmoff);
   float* const geo = (float*)(wbase + LY.off_geo);
   float* const dist = (float*)(wbase + LY.off_dist);
-  uint32_t* const rec = (uint32_t*)(wbase + LY.off_rec);
+  uint2* const rec = (uint2*)(wbase + LY.off_rec);
   uint8_t* const entmc = wbase + LY.off_entmc;
   uint8_t* const entlev = wbase + LY.off_entlev;
   uint8_t* const nmcnt = wbase + LY.off_nmcnt;
@@ -374,7 +381,7 @@ __global__ void __launch_bounds__(256, 2) pmnet_score_kernel(const KernelArgs ar
               for (int j = sm.cnode_off[k]; j < sm.cnode_off[k + 1]; ++j) M += (tm >> sm.ntype[sm.cnodes[j]]) & 1u;
               if (M > kMaxClusterNodes) toobig = true;
               if (M > 0) ++nrec;
-              if (M > 1) nml += M;
+              if (M > 4) nml += M;
             }
             if (nrec > 255) toobig = true;
           }
@@ -398,24 +405,25 @@ __global__ void __launch_bounds__(256, 2) pmnet_score_kernel(const KernelArgs ar
             const int c0 = B.cluster_node_off[q], c1 = B.cluster_node_off[q + 1];
             for (int i = c0; i < c1; ++i) {
               const unsigned tm = tmask[cl_nodes[i]];
-              int M = 0, first = 0;
+              int M = 0;
+              uint32_t packed = 0;
               for (int j = sm.cnode_off[k]; j < sm.cnode_off[k + 1]; ++j) {
                 const int mn = sm.cnodes[j];
                 if ((tm >> sm.ntype[mn]) & 1u) {
-                  if (M == 0) first = mn;
+                  if (M < 4) packed |= (uint32_t)mn << (8 * M);
                   ++M;
                 }
               }
               if (M == 0) continue;
-              uint32_t x = (uint32_t)first;
-              if (M > 1) {
+              uint32_t x = 0;
+              if (M > 4) {
                 x = mo;
                 for (int j = sm.cnode_off[k]; j < sm.cnode_off[k + 1]; ++j) {
                   const int mn = sm.cnodes[j];
                   if ((tm >> sm.ntype[mn]) & 1u) mlist[mo++] = (uint8_t)mn;
                 }
               }
-              rec[ro++] = (uint32_t)(nb + (i - c0)) | ((uint32_t)M << 8) | (x << 16);
+              rec[ro++] = make_uint2((uint32_t)(nb + (i - c0)) | ((uint32_t)M << 8) | (x << 16), packed);
             }
           }
           rec_used += trec;
@@ -465,10 +473,10 @@ __global__ void __launch_bounds__(256, 2) pmnet_score_kernel(const KernelArgs ar
             float sc = 0.0f;
             const uint32_t off = nmoff[e];
             for (int i = 0; i < cnt - 1; ++i) {
-              const uint32_t r1 = rec[off + i];
+              const uint2 r1 = rec[off + i];
               const float* drow = dist + ((size_t)rec_node(r1) * NL) * 32 + lane;
               for (int j = i + 1; j < cnt; ++j) {
-                const uint32_t r2 = rec[off + j];
+                const uint2 r2 = rec[off + j];
                 bool f;
                 sc += pair_term(sm, mlist, drow[(size_t)rec_node(r2) * 32], r1, r2, f);
               }
@@ -513,10 +521,10 @@ __global__ void __launch_bounds__(256, 2) pmnet_score_kernel(const KernelArgs ar
                   int nfail = 0;
                   bool dead = false;
                   for (int a = 0; a < cnt1; ++a) {
-                    const uint32_t r1 = rec[off1 + a];
+                    const uint2 r1 = rec[off1 + a];
                     const float* drow = dist + ((size_t)rec_node(r1) * NL) * 32 + lane;
                     for (int b = 0; b < cnt2; ++b) {
-                      const uint32_t r2 = rec[off2 + b];
+                      const uint2 r2 = rec[off2 + b];
                       bool f;
                       sc += pair_term(sm, mlist, drow[(size_t)rec_node(r2) * 32], r1, r2, f);
                       nfail += f ? 1 : 0;
@@ -597,11 +605,27 @@ __global__ void __launch_bounds__(256, 2) pmnet_score_kernel(const KernelArgs ar
                   st_cursor = found + 1;
                   st_nchild += 1;
                 }
+                // pair rows with the matched ancestors: lane dd looks up its own ancestor's row, then the rows
+                // are added in top-down order like the reference's running sums (tree.py:78-82)
+                const int myrow = (lane >= 1 && lane <= d && st_entry >= 0) ? prow[st_pbase + found] : -1;
+                unsigned anc = __ballot_sync(kFull, myrow >= 0);
                 float acc = 0.0f;
-                for (int dd = 1; dd <= d; ++dd) {
-                  const int en = __shfl_sync(kFull, st_entry, dd);
-                  const int pb = __shfl_sync(kFull, st_pbase, dd);
-                  if (en >= 0) acc += rows[(size_t)prow[pb + found] * 32 + lane];
+                while (anc) {
+                  // four independent row loads in flight per round; the adds stay in top-down order
+                  int rr[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const int dd = anc ? (__ffs(anc) - 1) : 0;
+                    const int r = __shfl_sync(kFull, myrow, dd);
+                    rr[u] = anc ? r : -1;
+                    anc &= anc - 1;
+                  }
+                  float vv[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) vv[u] = (rr[u] >= 0) ? rows[(size_t)rr[u] * 32 + lane] : 0.0f;
+#pragma unroll
+                  for (int u = 0; u < 4; ++u)
+                    if (rr[u] >= 0) acc += vv[u];
                 }
                 float t = ws.tot[tslot][lane];
                 const int sr = srow[found];
@@ -713,9 +737,10 @@ int sm_count_cached() {
 void resolve_cfg(const PmScoreConfig* in, PmScoreConfig* out, bool query_device) {
   PmScoreConfig c = {0, 0, 0, 0};
   if (in) c = *in;
-  if (c.warps_per_block <= 0) c.warps_per_block = 8;
-  if (c.warps_per_block > 8) c.warps_per_block = 8;
-  if (c.blocks <= 0) c.blocks = 2 * (query_device ? sm_count_cached() : 148);
+  constexpr int kMaxWarps = PM_BLOCK_THREADS / 32;
+  if (c.warps_per_block <= 0) c.warps_per_block = kMaxWarps;
+  if (c.warps_per_block > kMaxWarps) c.warps_per_block = kMaxWarps;
+  if (c.blocks <= 0) c.blocks = PM_MIN_BLOCKS * (query_device ? sm_count_cached() : 148);
   if (c.scratch_rows <= 0) c.scratch_rows = 8192;
   *out = c;
 }

@@ -113,6 +113,12 @@ def release_workspaces() -> None:
     _workspaces.clear()
 
 
+def workspace_bytes(model: "DeviceModel", config: "ScoreConfig | None" = None) -> int:
+    cfg = (config or ScoreConfig()).struct()
+    with torch.cuda.device(model.device):
+        return int(_lib.lib().pmnet_score_workspace_bytes(model.num_nodes, model.num_clusters, C.byref(cfg)))
+
+
 def score_batch(
     model: DeviceModel,
     batch: DeviceLigandBatch,
@@ -123,6 +129,7 @@ def score_batch(
     with_stats: bool = False,
     with_conf: bool = False,
     stream: torch.cuda.Stream | None = None,
+    workspace: torch.Tensor | None = None,
 ):
     """Enqueue one scoring launch on `stream` (default: torch's current stream). Returns a dict of device tensors:
     scores f32[n], status i32[n] (+ stats u32[n,4] -> {tree nodes, leaves, rows, pair entries}; conf f32[n,32])."""
@@ -132,7 +139,12 @@ def score_batch(
     cfg = (config or ScoreConfig()).struct()
     with torch.cuda.device(dev):
         need = L.pmnet_score_workspace_bytes(model.num_nodes, model.num_clusters, C.byref(cfg))
-        ws = _workspace(dev, need)
+        if workspace is None:
+            ws = _workspace(dev, need)
+        else:
+            ws = workspace
+            if ws.numel() < need:
+                raise RuntimeError(f"workspace of {ws.numel()} bytes is too small ({need} needed)")
         scores = out_scores if out_scores is not None else torch.empty(n, dtype=torch.float32, device=dev)
         status = out_status if out_status is not None else torch.empty(n, dtype=torch.int32, device=dev)
         stats = torch.zeros((n, 4), dtype=torch.int32, device=dev) if with_stats else None

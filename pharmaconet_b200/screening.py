@@ -19,7 +19,7 @@ import torch
 
 from . import _abi
 from .packing import LigandBatch, PackedModel
-from .scoring import DeviceLigandBatch, DeviceModel, ScoreConfig, big_config, score_batch, topk
+from .scoring import DeviceLigandBatch, DeviceModel, ScoreConfig, big_config, score_batch, topk, workspace_bytes
 
 
 def shard_blocks(n_ligands: int, rank: int, world: int, block_ligands: int) -> list[tuple[int, int]]:
@@ -93,6 +93,10 @@ class _Slot:
         self.t = {k: torch.empty(max(1, caps[k]), dtype=dtypes[k], device=device) for k in caps}
         self.ready = torch.cuda.Event()  # H2D finished
         self.free = torch.cuda.Event()  # kernel finished, slot reusable
+        # each slot scores on its own stream with its own scratch, so that the next block's warps back-fill the
+        # SMs while the previous block's longest ligands are still finishing (the tail of a persistent grid)
+        self.stream = torch.cuda.Stream(device)
+        self.workspace: torch.Tensor | None = None
 
 
 class Screener:
@@ -124,10 +128,11 @@ class Screener:
     def _timed_score(self, batch, **kw):
         if not self.record_kernel_events:
             return score_batch(self.model, batch, self.weights, self.config, **kw)
+        stream = kw.get("stream") or torch.cuda.current_stream(self.device)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(stream)
         out = score_batch(self.model, batch, self.weights, self.config, **kw)
-        e1.record()
+        e1.record(stream)
         self.kernel_events.append((e0, e1))
         return out
 
@@ -186,13 +191,21 @@ class Screener:
         n_conf = 0
         if blocks:
             self._ensure_slots(lib, blocks)
-        compute = torch.cuda.current_stream(dev)
+        main = torch.cuda.current_stream(dev)
+        start = torch.cuda.Event()
+        start.record(main)
+        need = workspace_bytes(self.model, self.config)
         pos = 0
+        spans = []
         for it, (a, b) in enumerate(blocks):
             slot = self._slots[it % 2]
+            if slot.workspace is None or slot.workspace.numel() < need:
+                slot.workspace = torch.empty(need, dtype=torch.uint8, device=dev)
             sl, bases = self._block_slices(lib, a, b)
             with torch.cuda.stream(self._copy_stream):
-                if it >= 2:
+                if it < 2:
+                    self._copy_stream.wait_event(start)
+                else:
                     self._copy_stream.wait_event(slot.free)
                 views = {}
                 for k, v in sl.items():
@@ -200,18 +213,28 @@ class Screener:
                     dst.copy_(torch.from_numpy(v), non_blocking=True)
                     views[k] = dst
                 slot.ready.record(self._copy_stream)
-            compute.wait_event(slot.ready)
             nb = b - a
             nc = int(lib.n_conf[a:b].sum())
             n_conf += nc
             db = DeviceLigandBatch(views, nb, nc, bases)
-            self._timed_score(db, out_scores=scores[pos : pos + nb], out_status=status[pos : pos + nb])
-            slot.free.record(compute)
-            ks, ki = topk(scores[pos : pos + nb], self.k, a)
+            if it < 2:
+                slot.stream.wait_event(start)
+            slot.stream.wait_event(slot.ready)
+            self._timed_score(
+                db, out_scores=scores[pos : pos + nb], out_status=status[pos : pos + nb],
+                stream=slot.stream, workspace=slot.workspace,
+            )  # fmt: skip
+            slot.free.record(slot.stream)
+            spans.append((pos, nb, a))
+            launches += 1
+            pos += nb
+        for slot in (self._slots or [])[: len(blocks)]:
+            main.wait_event(slot.free)
+        for p0, nb, a in spans:
+            ks, ki = topk(scores[p0 : p0 + nb], self.k, a)
             cand_s.append(ks)
             cand_i.append(ki)
-            launches += 3
-            pos += nb
+            launches += 2
         ids = np.concatenate([np.arange(a, b, dtype=np.int64) for a, b in blocks]) if blocks else np.zeros(0, np.int64)
         # ligands whose pair table overflowed the per-warp scratch: re-run them with the roomy configuration
         st = status.cpu().numpy()
