@@ -138,6 +138,21 @@ size_t pmnet_topk_workspace_bytes(int64_t n, int32_t k);
 int pmnet_topk(const float* scores, int64_t n, int64_t id_base, int32_t k, float* out_scores,
                int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream);
 
+/* 3x3x3 convolution, 96 -> 96 channels, stride 1, zero padding 1, fused per-channel scale/bias (folded
+ * BatchNorm3d in eval mode) and optional ReLU: replaces BaseConv3d.forward (src/pmnet/network/nn/layers.py:45-46)
+ * for the shape used by FPNDecoder (decoders/fpn_decoder.py:54-66), CavityHead (cavity_head.py:18-37) and the
+ * MaskHead decoder (mask_head.py:38-80). tcgen05 implicit GEMM, bf16 operands, fp32 accumulation.
+ *   x_c8, y_c8 : bf16 [B][12][D][H][W][8]  (8-channel chunks; channel c = chunk*8 + lane)
+ *   w_packed   : bf16 [27][12][96][8]      (tap = (kd*3 + kh)*3 + kw, then C_in chunk, C_out, 8 C_in lanes)
+ *   scale,bias : fp32 [96]
+ *   head_w/head_b/head_out : optional fused 1x1 conv to ONE channel applied to the activated output
+ *                (cavity_head.py:26,36): head_out fp32 [B][D][H][W]; y_c8 may then be NULL to skip the store
+ *   planes_per_item : output d-planes per work item (even; 0 = 16), max_ctas : 0 = one per SM
+ * D must be even. */
+int pmnet_conv3d_k3_c96(const void* x_c8, const void* w_packed, const float* scale, const float* bias, void* y_c8,
+                        const float* head_w, float head_b, float* head_out, int32_t B, int32_t D, int32_t H,
+                        int32_t W, int32_t relu, int32_t planes_per_item, int32_t max_ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

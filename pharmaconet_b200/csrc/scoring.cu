@@ -747,6 +747,9 @@ void resolve_cfg(const PmScoreConfig* in, PmScoreConfig* out, bool query_device)
 
 }  // namespace
 
+// shared by the other translation units of the library
+void pmnet_set_error(const char* msg) { set_err(msg); }
+
 extern "C" {
 
 int pmnet_abi_version(void) { return PMNET_ABI_VERSION; }
