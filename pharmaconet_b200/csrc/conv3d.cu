@@ -250,35 +250,47 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_k3_c96_kernel(const __grid
           const uint32_t buf = gseq & 1;
           mbar_wait(bar(BAR_AEMPTY + buf), ((gseq >> 1) & 1) ^ 1);
           tc_fence_after();
-          for (int tap = 0; tap < kTaps; ++tap) {
-            const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-            if (tap == 0) {
+          // descriptors are {hi, lo}: hi is constant per operand, lo = start >> 4 | (LBO >> 4) << 16, so moving the
+          // window by a tap or a K step is one 32-bit add with an immediate
+          constexpr uint32_t kAHi = (uint32_t)(kRowBytes >> 4) | (1u << 14);
+          constexpr uint32_t kBHi = (uint32_t)(128 >> 4) | (1u << 14);
+#pragma unroll 1
+          for (int kd = 0; kd < 3; ++kd) {
+            if (kd == 0) {
               wait_plane(d0 - 1);
               wait_plane(d0);
-            } else if (tap == 9) {
-              wait_plane(d0 + 1);
-            } else if (tap == 18) {
-              wait_plane(d0 + 2);
+            } else {
+              wait_plane(d0 + kd);
             }
-            const uint32_t st = wseq % kWStages;
-            mbar_wait(bar(BAR_WFULL + st), (wseq / kWStages) & 1);
-            ++wseq;
-            tc_fence_after();
-            const uint32_t wb = sbase + kSmemWeights + st * kTapBytes;
+            uint32_t a_lo[2];
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               const uint32_t slot = plane_seq(d0 + g + kd - 1) % kPlaneSlots;
-              const uint32_t ab = sbase + kSmemPlanes + slot * kPlaneBytes + kh * kRowBytes + kw * 16;
-              const uint32_t tacc = tmem_base + (buf * 2 + g) * 128;
-#pragma unroll
-              for (int ks = 0; ks < kKSteps; ++ks) {
-                const uint64_t ad = make_desc(ab + 2 * ks * kChunkBytes, kChunkBytes, kRowBytes);
-                const uint64_t bd = make_desc(wb + 2 * ks * (kC * 16), kC * 16, 128);
-                tc_mma(tacc, ad, bd, kIdesc, (tap | ks) != 0);
-              }
+              a_lo[g] = ((sbase + kSmemPlanes + slot * kPlaneBytes) >> 4) | ((uint32_t)(kChunkBytes >> 4) << 16);
             }
-            tc_commit(bar(BAR_WEMPTY + st));
-            if (tap == 8) {
+#pragma unroll
+            for (int khw = 0; khw < 9; ++khw) {
+              const int kh = khw / 3, kw = khw % 3;
+              const uint32_t st = wseq & (kWStages - 1);
+              mbar_wait(bar(BAR_WFULL + st), (wseq / kWStages) & 1);
+              ++wseq;
+              tc_fence_after();
+              const uint32_t b_lo = ((sbase + kSmemWeights + st * kTapBytes) >> 4) | ((uint32_t)((kC * 16) >> 4) << 16);
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                const uint32_t tacc = tmem_base + (buf * 2 + g) * 128;
+#pragma unroll
+                for (int ks = 0; ks < kKSteps; ++ks) {
+                  const uint32_t al = a_lo[g] + (uint32_t)((kh * kRowBytes + kw * 16 + 2 * ks * kChunkBytes) >> 4);
+                  const uint32_t bl = b_lo + (uint32_t)((2 * ks * kC * 16) >> 4);
+                  const uint64_t ad = ((uint64_t)kAHi << 32) | al;
+                  const uint64_t bd = ((uint64_t)kBHi << 32) | bl;
+                  tc_mma(tacc, ad, bd, kIdesc, (kd | khw | ks) != 0);
+                }
+              }
+              tc_commit(bar(BAR_WEMPTY + st));
+            }
+            if (kd == 0) {
               release_plane(d0 - 1);
               release_plane(d0);
             }
