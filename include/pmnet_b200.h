@@ -153,6 +153,34 @@ int pmnet_conv3d_k3_c96(const void* x_c8, const void* w_packed, const float* sca
                         const float* head_w, float head_b, float* head_out, int32_t B, int32_t D, int32_t H,
                         int32_t W, int32_t relu, int32_t planes_per_item, int32_t max_ctas, void* stream);
 
+/* FPNDecoder lateral (decoders/fpn_decoder.py:100-111): out = act(scale * (W x) + bias) + nearest_upsample(up).
+ *   x      : fp32 [B][C_in][D][H][W] (x_is_c8 = 0) or bf16 c8 [B][C_in/8][D][H][W][8] (x_is_c8 = 1)
+ *   w_t    : fp32 [C_in][96] (the 1x1 conv weight, transposed); scale/bias fp32 [96] or NULL for a raw linear map
+ *   up_c8  : optional bf16 c8 [B][12][D/2][H/2][W/2][8], added after the activation; out_c8 bf16 c8 [B][12][D][H][W][8] */
+int pmnet_lateral_c96(const void* x, int32_t x_is_c8, int32_t c_in, const float* w_t, const float* scale,
+                      const float* bias, int32_t relu, const void* up_c8, void* out_c8, int32_t B, int32_t D,
+                      int32_t H, int32_t W, void* stream);
+
+/* MaskHead.get_box_features (mask_head.py:170-196) pushed through the linear lateral conv: for every box j of a group
+ *   out[j] = act(scale * (S + u[j] + [voxel in pvox] pvec[j]) + bias) + nearest_upsample(up[j])
+ *   s_c8 : bf16 c8 [12][D][H][W][8] shared by the group (the lateral conv of the pocket's feature map, or the feature
+ *          map itself at the top level where the lateral is the identity: then scale = bias = NULL, relu = 0)
+ *   u, pvec : fp32 [nbox][96]; pvox int32 [n_pvox] flat voxel ids of ALL token voxels of the group (every box gets
+ *          its own pvec at all of them - the reference's broadcasting)
+ *   up_c8 : optional bf16 c8 [nbox][12][D/2][H/2][W/2][8]; out_c8 bf16 c8 [nbox][12][D][H][W][8] */
+int pmnet_box_combine_c96(const void* s_c8, const float* u, const float* pvec, const int32_t* pvox, int32_t n_pvox,
+                          const float* scale, const float* bias, int32_t relu, const void* up_c8, void* out_c8,
+                          int32_t nbox, int32_t D, int32_t H, int32_t W, void* stream);
+
+/* Density-map post-processing (module.py:277-288): sigmoid(logits) masked to box & protein & cavity, 5^3 Gaussian
+ * smoothing with zero padding (utils/smoothing.py), masked again, values < threshold set to 0. The spherical box area of
+ * token (x, y, z, type) (data/token_inference.py:118-146) is evaluated in place.
+ *   logits fp32 [n][size^3]; tokens int32 [n][4]; masks uint8 [size^3]; taps3 HOST fp32 [3] = 1-D Gaussian taps at
+ *   distance 2, 1, 0 (normalised); out fp32 [n][size^3] */
+int pmnet_density_post(const float* logits, const int32_t* tokens, const uint8_t* protein_mask,
+                       const uint8_t* cavity_mask, const float* taps3, float threshold, float* out, int32_t n,
+                       int32_t size, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ from . import _abi
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("PMNET_B200_SO") or os.path.join(_PKG, "libpmnet_b200.so")  # env override: developer A/B builds
-SOURCES = [os.path.join(_PKG, "csrc", "scoring.cu"), os.path.join(_PKG, "csrc", "conv3d.cu")]
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("scoring.cu", "conv3d.cu", "pointwise.cu")]
 HEADERS = [os.path.join(_ROOT, "include", "pmnet_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -85,6 +85,21 @@ def lib() -> C.CDLL:
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
     ]  # fmt: skip
+    L.pmnet_lateral_c96.restype = C.c_int
+    L.pmnet_lateral_c96.argtypes = [
+        C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+    ]  # fmt: skip
+    L.pmnet_box_combine_c96.restype = C.c_int
+    L.pmnet_box_combine_c96.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+        C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+    ]  # fmt: skip
+    L.pmnet_density_post.restype = C.c_int
+    L.pmnet_density_post.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int32, C.c_int32,
+        C.c_void_p,
+    ]  # fmt: skip
     _lib = L
     return L
 
@@ -103,4 +118,7 @@ EXPORTS = (
     "pmnet_topk_workspace_bytes",
     "pmnet_topk",
     "pmnet_conv3d_k3_c96",
+    "pmnet_lateral_c96",
+    "pmnet_box_combine_c96",
+    "pmnet_density_post",
 )

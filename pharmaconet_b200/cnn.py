@@ -1,0 +1,270 @@
+"""The reference's `PharmacoNetModel` (src/pmnet/network/detector.py:12-91) for inference on B200.
+
+Same four entry points with the same tensor signatures - `forward_feature`, `forward_cavity_extraction`,
+`forward_token_prediction`, `forward_segmentation` - built from a reference-format state dict (the `model` entry of
+the reference's `model.tar`, module.py:82-85). The convolution stack (FPN decoder, cavity head, mask head: ~90 % of
+the FLOPs) runs on the tcgen05 kernel of csrc/conv3d.cu with BatchNorm(eval) folded in; the glue between the
+convolutions is csrc/pointwise.cu; the Swin backbone and the token MLPs are plain fp32 GEMMs through torch.
+Activations between convolutions are bf16 in the 8-channel-chunk layout; accumulation is fp32.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from collections.abc import Sequence
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib, conv
+from .swin import SwinV2Backbone
+
+_FEATURE_CHANNELS = (33, 96, 192, 384, 768)  # builder.py:27
+_NUM_CONVS = (1, 2, 2, 2, 2)
+
+
+def _stream(dev) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class _ConvBN:
+    """Folded BaseConv3d (nn/layers.py:4-46): conv weight + per-channel scale / bias."""
+
+    def __init__(self, sd, prefix: str):
+        w = sd[prefix + "_conv.weight"]
+        self.kernel = w.shape[2]
+        self.cin = w.shape[1]
+        if prefix + "_norm.weight" in sd:
+            self.scale, self.bias = conv.fold_bn(
+                sd.get(prefix + "_conv.bias"), sd[prefix + "_norm.weight"], sd[prefix + "_norm.bias"],
+                sd[prefix + "_norm.running_mean"], sd[prefix + "_norm.running_var"],
+            )  # fmt: skip
+        else:
+            self.scale = torch.ones(w.shape[0], dtype=torch.float32, device=w.device)
+            self.bias = sd[prefix + "_conv.bias"].float().contiguous()
+        self.weight = w
+        if self.kernel == 3 and self.cin == 96 and w.shape[0] == 96:
+            self.packed = conv.pack_weights_k3(w)
+        elif self.kernel == 1:
+            self.w_t = w.reshape(w.shape[0], self.cin).t().contiguous().float()  # [C_in][C_out]
+
+
+class Features(tuple):
+    """multi-scale features, top-down, as NCDHW fp32 tensors (the reference's return type); `.c8` keeps the bf16
+    chunked copies the kernels consume so that later stages do not convert again."""
+
+    c8: list[torch.Tensor]
+
+
+class PharmacoNetModel:
+    def __init__(self, state_dict: dict[str, torch.Tensor], device="cuda"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("pharmaconet_b200.cnn runs on CUDA devices only (no CPU fallback)")
+        sd = {k: v.to(self.device) for k, v in state_dict.items()}
+        self.sd = sd
+        self.backbone = SwinV2Backbone(sd, "embedding.backbone.")
+        self.num_interactions = sd["token_head.interaction_embedding.weight"].shape[0]
+        dec = "embedding.decoder."
+        self.fpn_lateral = [_ConvBN(sd, f"{dec}lateral_conv_list.{l}.") if l < 4 else None for l in range(5)]
+        self.fpn_convs = [[_ConvBN(sd, f"{dec}fpn_convs_list.{l}.{i}.") for i in range(_NUM_CONVS[l])] for l in range(5)]
+        self.cavity = {
+            name: (_ConvBN(sd, f"cavity_head.{name}.0."), _ConvBN(sd, f"cavity_head.{name}.1."))
+            for name in ("short_head", "long_head")
+        }
+        mdec = "mask_head.decoder."
+        self.mask_lateral = [_ConvBN(sd, f"{mdec}lateral_conv_list.{l}.") if l < 4 else None for l in range(5)]
+        self.mask_convs = [[_ConvBN(sd, f"{mdec}fpn_convs_list.{l}.{i}.") for i in range(_NUM_CONVS[l])] for l in range(5)]
+        self.mask_logit_w = sd["mask_head.conv_logits.weight"].reshape(96).float().contiguous()
+        self.mask_logit_b = float(sd["mask_head.conv_logits.bias"].item())
+        self._L = _lib.lib()
+
+    # ------------------------------------------------------------------ kernels
+    def _k3(self, x_c8, layer: _ConvBN, head=None, store_out=True):
+        hw, hb = head if head is not None else (None, 0.0)
+        return conv.conv3d_k3_c96(x_c8, layer.packed, layer.scale, layer.bias, True, hw, hb, store_out)
+
+    def _lateral(self, x, x_is_c8: bool, layer: _ConvBN, up_c8, affine=True):
+        if x_is_c8:
+            B, _, D, H, W, _ = x.shape
+        else:
+            B, _, D, H, W = x.shape
+            x = x.contiguous().float()
+        out = torch.empty((B, 12, D, H, W, 8), dtype=torch.bfloat16, device=self.device)
+        rc = self._L.pmnet_lateral_c96(
+            x.data_ptr(), int(x_is_c8), layer.cin, layer.w_t.data_ptr(),
+            layer.scale.data_ptr() if affine else None, layer.bias.data_ptr() if affine else None, int(affine),
+            up_c8.data_ptr() if up_c8 is not None else None, out.data_ptr(), B, D, H, W, _stream(self.device),
+        )  # fmt: skip
+        _lib.check(rc, "pmnet_lateral_c96")
+        return out
+
+    def _combine(self, s_c8, u, pvec, pvox, layer: _ConvBN | None, up_c8):
+        nbox = u.shape[0]
+        _, D, H, W, _ = s_c8.shape
+        out = torch.empty((nbox, 12, D, H, W, 8), dtype=torch.bfloat16, device=self.device)
+        rc = self._L.pmnet_box_combine_c96(
+            s_c8.data_ptr(), u.data_ptr(), pvec.data_ptr(), pvox.data_ptr(), pvox.numel(),
+            layer.scale.data_ptr() if layer is not None else None, layer.bias.data_ptr() if layer is not None else None,
+            int(layer is not None), up_c8.data_ptr() if up_c8 is not None else None, out.data_ptr(),
+            nbox, D, H, W, _stream(self.device),
+        )  # fmt: skip
+        _lib.check(rc, "pmnet_box_combine_c96")
+        return out
+
+    # ------------------------------------------------------------------ detector.py:36-43
+    @torch.no_grad()
+    def forward_feature(self, in_image: torch.Tensor) -> Features:
+        image = in_image.to(self.device, torch.float32).contiguous()
+        bottom_up = [image, *self.backbone.forward(image)]
+        # FPNDecoder.forward (decoders/fpn_decoder.py:86-115), top (4^3) to bottom (64^3)
+        top = self.fpn_convs[4][0]
+        y = F.conv3d(bottom_up[4], top.weight, padding=1)  # 768 -> 96 at 4^3: 0.25 GFLOP, left to cuDNN
+        y = torch.relu(y * top.scale.view(1, -1, 1, 1, 1) + top.bias.view(1, -1, 1, 1, 1))
+        fpn = self._k3(conv.to_c8(y), self.fpn_convs[4][1])[0]
+        outs = [fpn]
+        for level in (3, 2, 1, 0):
+            fpn = self._lateral(bottom_up[level], False, self.fpn_lateral[level], fpn)
+            for layer in self.fpn_convs[level]:
+                fpn = self._k3(fpn, layer)[0]
+            outs.append(fpn)
+        nchw = []
+        for o in outs:
+            t = conv.from_c8(o)
+            t._pm_c8 = o  # the bf16 chunked twin travels with the tensor: later stages skip the conversion
+            nchw.append(t)
+        feats = Features(nchw)
+        feats.c8 = outs
+        return feats
+
+    def _as_c8(self, t: torch.Tensor) -> torch.Tensor:
+        """NCDHW feature tensor -> bf16 c8 (free when the tensor came out of forward_feature)."""
+        twin = getattr(t, "_pm_c8", None)
+        if twin is not None:
+            return twin
+        if t.dim() == 6:
+            return t
+        return conv.to_c8(t.to(self.device))
+
+    # ------------------------------------------------------------------ detector.py:45-53, cavity_head.py:45-60
+    @torch.no_grad()
+    def forward_cavity_extraction(self, features) -> tuple[torch.Tensor, torch.Tensor]:
+        x = self._as_c8(features)
+        outs = []
+        for name in ("short_head", "long_head"):
+            k3, k1 = self.cavity[name]
+            hw = k1.weight.reshape(96).float().contiguous()
+            _, logits = self._k3(x, k3, head=(hw, float(k1.bias.item())), store_out=False)
+            outs.append(logits.unsqueeze(1))
+        return outs[0], outs[1]
+
+    # ------------------------------------------------------------------ detector.py:55-71, token_head.py:50-86
+    @torch.no_grad()
+    def forward_token_prediction(self, features, tokens_list: Sequence[torch.Tensor]):
+        sd = self.sd
+        x = self._as_c8(features)
+        scores, feats = [], []
+        for b, tokens in enumerate(tokens_list):
+            tokens = tokens.to(self.device, torch.long)
+            if tokens.shape[0] == 0:
+                tf = torch.empty((0, 192), dtype=torch.float32, device=self.device)
+            else:
+                xs, ys, zs, it = tokens.unbind(1)
+                voxel = x[b][:, xs, ys, zs, :].permute(1, 0, 2).reshape(-1, 96).float()
+                h0 = torch.cat([voxel, sd["token_head.interaction_embedding.weight"][it]], dim=1)
+                skip = (
+                    F.linear(h0, sd["token_head.skip.weight"], sd["token_head.skip.bias"])
+                    if "token_head.skip.weight" in sd
+                    else h0
+                )
+                h = h0
+                for i in (0, 2, 4):
+                    h = F.silu(F.linear(h, sd[f"token_head.feature_mlp.{i}.weight"], sd[f"token_head.feature_mlp.{i}.bias"]))
+                tf = skip + h
+            s = tf
+            for i in (0, 2):
+                s = torch.relu(F.linear(s, sd[f"token_head.score_mlp.{i}.weight"], sd[f"token_head.score_mlp.{i}.bias"]))
+            s = F.linear(s, sd["token_head.score_mlp.4.weight"], sd["token_head.score_mlp.4.bias"]).squeeze(-1)
+            scores.append(s)
+            feats.append(tf)
+        return scores, feats
+
+    # ------------------------------------------------------------------ detector.py:73-91, mask_head.py:38-196
+    def _shared_laterals(self, features, b: int):
+        """conv1x1 of the pocket's feature maps for the mask-head decoder: linear, shared by every box of pocket b."""
+        cache = getattr(features, "_mask_lateral_cache", None)
+        if cache is None:
+            cache = {}
+            try:
+                features._mask_lateral_cache = cache
+            except AttributeError:
+                pass
+        if b not in cache:
+            per_level = []
+            for level in range(5):  # bottom-up level = 4 - top-down index
+                f = self._as_c8(features[4 - level])[b : b + 1]
+                per_level.append(f[0] if level == 4 else self._lateral(f, True, self.mask_lateral[level], None, affine=False)[0])
+            cache[b] = per_level
+        return cache[b]
+
+    @torch.no_grad()
+    def forward_segmentation(self, multi_scale_features, box_tokens_list, box_token_features_list, return_aux=False):
+        if return_aux:
+            raise NotImplementedError("auxiliary multi-scale masks are a training-time output of the reference")
+        sd = self.sd
+        out_masks = []
+        for b, (tokens, tfeat) in enumerate(zip(box_tokens_list, box_token_features_list)):
+            tokens = tokens.to(self.device, torch.long)
+            nbox = tokens.shape[0]
+            size = multi_scale_features[4].shape[2]
+            if nbox == 0:
+                out_masks.append(torch.empty((0, size, size, size), dtype=torch.float32, device=self.device))
+                continue
+            tfeat = tfeat.to(self.device, torch.float32)
+            shared = self._shared_laterals(multi_scale_features, b)
+            fpn = None
+            for level in (4, 3, 2, 1, 0):
+                s = shared[level]
+                D = s.shape[1]
+                div = size // D
+                vox = ((tokens[:, 0] // div) * D + tokens[:, 1] // div) * D + tokens[:, 2] // div
+                pvox = torch.unique(vox).to(torch.int32)
+                bg = F.linear(tfeat, sd[f"mask_head.background_mlp_list.{level}.weight"], sd[f"mask_head.background_mlp_list.{level}.bias"])
+                pt = F.linear(tfeat, sd[f"mask_head.point_mlp_list.{level}.weight"], sd[f"mask_head.point_mlp_list.{level}.bias"])
+                lat = self.mask_lateral[level]
+                if lat is not None:  # push the per-box vectors through the (linear) 1x1 conv
+                    wl = lat.weight.reshape(96, 96).float()
+                    bg, pt = bg @ wl.t(), pt @ wl.t()
+                fpn = self._combine(s, bg.contiguous(), pt.contiguous(), pvox, lat, fpn)
+                convs = self.mask_convs[level]
+                for i, layer in enumerate(convs):
+                    if level == 0 and i == len(convs) - 1:
+                        _, logits = self._k3(fpn, layer, head=(self.mask_logit_w, self.mask_logit_b), store_out=False)
+                    else:
+                        fpn = self._k3(fpn, layer)[0]
+            out_masks.append(logits)
+        return out_masks, None
+
+
+def density_post(logits, tokens, protein_mask, cavity_mask, threshold: float = 0.5):
+    """module.py:277-288 on the device: sigmoid, box/protein/cavity mask, 5^3 Gaussian, mask, threshold."""
+    import math
+
+    dev = logits.device
+    n, S = logits.shape[0], logits.shape[-1]
+    out = torch.empty((n, S, S, S), dtype=torch.float32, device=dev)
+    if n == 0:
+        return out
+    w = [math.exp(-0.5 * (d / 0.5) ** 2) for d in (2, 1, 0)]
+    tot = 2 * w[0] + 2 * w[1] + w[2]
+    taps = (C.c_float * 3)(*[v / tot for v in w])
+    lg = logits.contiguous().float()
+    tk = tokens.to(dev, torch.int32).contiguous()
+    pm = protein_mask.to(dev).reshape(-1).to(torch.uint8).contiguous()
+    cm = cavity_mask.to(dev).reshape(-1).to(torch.uint8).contiguous()
+    rc = _lib.lib().pmnet_density_post(
+        lg.data_ptr(), tk.data_ptr(), pm.data_ptr(), cm.data_ptr(), taps, C.c_float(threshold), out.data_ptr(), n, S,
+        _stream(dev),
+    )  # fmt: skip
+    _lib.check(rc, "pmnet_density_post")
+    return out

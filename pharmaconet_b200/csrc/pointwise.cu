@@ -1,0 +1,286 @@
+// pointwise.cu - the memory-bound glue around the tcgen05 convolutions of the CNN forward, one pass each over the
+// 8-channel-chunk ("c8") bf16 activations. None of these is GEMM-heavy enough to be worth tensor cores; they are
+// written for coalesced 16 B accesses and are HBM/L2 bound.
+//
+//  pmnet_lateral_c96      FPNDecoder lateral: 1x1 conv (C_in -> 96) + BatchNorm(eval) + ReLU, then
+//                         "+ nearest-upsampled coarser level"      src/pmnet/network/decoders/fpn_decoder.py:100-111
+//  pmnet_box_combine_c96  MaskHead.get_box_features folded through the (linear) lateral 1x1 conv of the mask-head
+//                         decoder: the conv of the shared feature map is computed once per pocket, each box adds
+//                         its background / point vectors                 src/pmnet/network/mask_head.py:170-196
+//  pmnet_density_post     sigmoid -> mask -> 5^3 Gaussian (sigma 0.5 voxel, zero pad) -> mask -> threshold, with the
+//                         spherical box area computed in place          src/pmnet/module.py:277-288,
+//                         src/pmnet/utils/smoothing.py:17-71, src/pmnet/data/token_inference.py:118-146
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pmnet_b200.h"
+
+extern void pmnet_set_error(const char* msg);
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& p, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 p;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+// ------------------------------------------------------------------ lateral 1x1 conv
+// grid: (ceil(V / 64), B); block 128 = 64 voxels x 2 halves of 48 output channels. Weights [C_in][96] fp32 in smem.
+template <int IN_C8>
+__global__ void __launch_bounds__(128) lateral_kernel(const void* __restrict__ x, int cin, const float* __restrict__ wt,
+                                                      const float* __restrict__ scale, const float* __restrict__ bias,
+                                                      int relu, const uint4* __restrict__ up, uint4* __restrict__ out,
+                                                      int D, int H, int W) {
+  extern __shared__ float sw[];  // [cin][96]
+  const int V = D * H * W;
+  for (int i = threadIdx.x; i < cin * 96; i += blockDim.x) sw[i] = wt[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int v = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int half = threadIdx.x >> 6;
+  if (v >= V) return;
+  float acc[48];
+#pragma unroll
+  for (int c = 0; c < 48; ++c) acc[c] = 0.0f;
+  if (IN_C8) {
+    const uint4* xp = reinterpret_cast<const uint4*>(x) + (size_t)b * (cin / 8) * V + v;
+    for (int q = 0; q < cin / 8; ++q) {
+      float f[8];
+      unpack8(__ldg(xp + (size_t)q * V), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float* wr = sw + (q * 8 + j) * 96 + half * 48;
+#pragma unroll
+        for (int c = 0; c < 48; ++c) acc[c] = fmaf(f[j], wr[c], acc[c]);
+      }
+    }
+  } else {
+    const float* xp = reinterpret_cast<const float*>(x) + (size_t)b * cin * V + v;
+    for (int k = 0; k < cin; ++k) {
+      const float xv = __ldg(xp + (size_t)k * V);
+      const float* wr = sw + k * 96 + half * 48;
+#pragma unroll
+      for (int c = 0; c < 48; ++c) acc[c] = fmaf(xv, wr[c], acc[c]);
+    }
+  }
+  const int w = v % W, h = (v / W) % H, d = v / (W * H);
+  const int Vu = (D / 2) * (H / 2) * (W / 2);
+  const int vu = ((d >> 1) * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1);
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const int chunk = half * 6 + q;
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = chunk * 8 + j;
+      float t = acc[q * 8 + j];
+      if (scale) t = fmaf(t, __ldg(scale + c), __ldg(bias + c));
+      if (relu) t = fmaxf(t, 0.0f);
+      y[j] = t;
+    }
+    if (up) {
+      float u[8];
+      unpack8(__ldg(up + ((size_t)b * 12 + chunk) * Vu + vu), u);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] += u[j];
+    }
+    out[((size_t)b * 12 + chunk) * V + v] = pack8(y);
+  }
+}
+
+// ------------------------------------------------------------------ per-box combine
+// out[j] = act(scale * (S + u_j + [v in P] p_j) + bias) + up_j ; thread = (voxel, chunk), loops over boxes.
+__global__ void __launch_bounds__(256) box_combine_kernel(const uint4* __restrict__ S, const float* __restrict__ u,
+                                                          const float* __restrict__ pvec, const int* __restrict__ pvox,
+                                                          int n_pvox, const float* __restrict__ scale,
+                                                          const float* __restrict__ bias, int relu,
+                                                          const uint4* __restrict__ up, uint4* __restrict__ out,
+                                                          int nbox, int D, int H, int W) {
+  const int V = D * H * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // chunk * V + v
+  if (idx >= (size_t)12 * V) return;
+  const int chunk = (int)(idx / V), v = (int)(idx % V);
+  float s[8];
+  unpack8(__ldg(S + idx), s);
+  bool at_point = false;
+  for (int i = 0; i < n_pvox; ++i) at_point |= (pvox[i] == v);
+  const int w = v % W, h = (v / W) % H, d = v / (W * H);
+  const int Vu = (D / 2) * (H / 2) * (W / 2);
+  const int vu = ((d >> 1) * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1);
+  for (int j = 0; j < nbox; ++j) {
+    float y[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = chunk * 8 + k;
+      float t = s[k] + __ldg(u + j * 96 + c);
+      if (at_point) t += __ldg(pvec + j * 96 + c);
+      if (scale) t = fmaf(t, __ldg(scale + c), __ldg(bias + c));
+      if (relu) t = fmaxf(t, 0.0f);
+      y[k] = t;
+    }
+    if (up) {
+      float uu[8];
+      unpack8(__ldg(up + ((size_t)j * 12 + chunk) * Vu + vu), uu);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) y[k] += uu[k];
+    }
+    out[((size_t)j * 12 + chunk) * V + v] = pack8(y);
+  }
+}
+
+// ------------------------------------------------------------------ density-map post-processing
+// INTERACTION_DIST (src/pmnet/data/constant.py:28-39) -> ceil((dist + 1.0) / 0.5) voxels
+__constant__ int kBoxRadius[10] = {11, 14, 14, 15, 15, 11, 11, 14, 14, 11};
+
+__device__ __forceinline__ bool available(int x, int y, int z, int tx, int ty, int tz, int r2, const uint8_t* prot,
+                                          const uint8_t* cav, int S) {
+  const int dx = x - tx, dy = y - ty, dz = z - tz;
+  if (dx * dx + dy * dy + dz * dz >= r2) return false;  // |g - t| < threshold (token_inference.py:144-145)
+  const int v = (x * S + y) * S + z;
+  return prot[v] && cav[v];
+}
+
+// grid: (S^3 / 256, n maps). logits [n][S^3]; tokens int32 [n][4] (x, y, z, type); masks uint8 [S^3]; w5[5] = 1-D
+// normalised Gaussian taps (the 3-D kernel of smoothing.py is their outer product).
+__global__ void __launch_bounds__(256) density_post_kernel(const float* __restrict__ logits, const int* __restrict__ tokens,
+                                                           const uint8_t* __restrict__ prot, const uint8_t* __restrict__ cav,
+                                                           float w0, float w1, float w2, float threshold,
+                                                           float* __restrict__ out, int S) {
+  const int n = blockIdx.y;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int V = S * S * S;
+  if (v >= V) return;
+  const int tx = tokens[n * 4 + 0], ty = tokens[n * 4 + 1], tz = tokens[n * 4 + 2], tt = tokens[n * 4 + 3];
+  const int r = kBoxRadius[tt], r2 = r * r;
+  const int z = v % S, y = (v / S) % S, x = v / (S * S);
+  float res = 0.0f;
+  if (available(x, y, z, tx, ty, tz, r2, prot, cav, S)) {
+    const float wk[5] = {w0, w1, w2, w1, w0};
+    const float* lg = logits + (size_t)n * V;
+    float acc = 0.0f;
+    for (int a = -2; a <= 2; ++a) {
+      const int xa = x + a;
+      if (xa < 0 || xa >= S) continue;
+      for (int bq = -2; bq <= 2; ++bq) {
+        const int yb = y + bq;
+        if (yb < 0 || yb >= S) continue;
+        const float wab = wk[a + 2] * wk[bq + 2];
+        for (int c = -2; c <= 2; ++c) {
+          const int zc = z + c;
+          if (zc < 0 || zc >= S) continue;
+          if (!available(xa, yb, zc, tx, ty, tz, r2, prot, cav, S)) continue;
+          const float p = 1.0f / (1.0f + expf(-lg[(xa * S + yb) * S + zc]));
+          acc = fmaf(wab * wk[c + 2], p, acc);
+        }
+      }
+    }
+    res = (acc < threshold) ? 0.0f : acc;
+  }
+  out[(size_t)n * V + v] = res;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pmnet_lateral_c96(const void* x, int32_t x_is_c8, int32_t c_in, const float* w_t, const float* scale,
+                      const float* bias, int32_t relu, const void* up_c8, void* out_c8, int32_t B, int32_t D,
+                      int32_t H, int32_t W, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!x || !w_t || !out_c8 || (scale && !bias)) {
+    pmnet_set_error("pmnet_lateral_c96: null argument");
+    return PMNET_EINVAL;
+  }
+  if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || c_in <= 0 || (x_is_c8 && (c_in & 7)) || (up_c8 && ((D | H | W) & 1))) {
+    pmnet_set_error("pmnet_lateral_c96: bad shape");
+    return PMNET_EINVAL;
+  }
+  const size_t smem = (size_t)c_in * 96 * 4;
+  if (smem > 200 * 1024) {
+    pmnet_set_error("pmnet_lateral_c96: C_in too large for the shared-memory weight tile");
+    return PMNET_ELIMIT;
+  }
+  const int V = D * H * W;
+  dim3 grid((V + 63) / 64, B);
+  cudaError_t e;
+  if (x_is_c8) {
+    e = cudaFuncSetAttribute(lateral_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      lateral_kernel<1><<<grid, 128, smem, stream>>>(x, c_in, w_t, scale, bias, relu, (const uint4*)up_c8, (uint4*)out_c8,
+                                                     D, H, W);
+  } else {
+    e = cudaFuncSetAttribute(lateral_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      lateral_kernel<0><<<grid, 128, smem, stream>>>(x, c_in, w_t, scale, bias, relu, (const uint4*)up_c8, (uint4*)out_c8,
+                                                     D, H, W);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    pmnet_set_error(cudaGetErrorString(e));
+    return PMNET_ECUDA;
+  }
+  return PMNET_OK;
+}
+
+int pmnet_box_combine_c96(const void* s_c8, const float* u, const float* pvec, const int32_t* pvox, int32_t n_pvox,
+                          const float* scale, const float* bias, int32_t relu, const void* up_c8, void* out_c8,
+                          int32_t nbox, int32_t D, int32_t H, int32_t W, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!s_c8 || !u || !out_c8 || (n_pvox > 0 && (!pvec || !pvox)) || (scale && !bias)) {
+    pmnet_set_error("pmnet_box_combine_c96: null argument");
+    return PMNET_EINVAL;
+  }
+  if (nbox <= 0 || D <= 0 || H <= 0 || W <= 0 || n_pvox < 0 || (up_c8 && ((D | H | W) & 1))) {
+    pmnet_set_error("pmnet_box_combine_c96: bad shape");
+    return PMNET_EINVAL;
+  }
+  const size_t total = (size_t)12 * D * H * W;
+  box_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      (const uint4*)s_c8, u, pvec, pvox, n_pvox, scale, bias, relu, (const uint4*)up_c8, (uint4*)out_c8, nbox, D, H, W);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    pmnet_set_error(cudaGetErrorString(e));
+    return PMNET_ECUDA;
+  }
+  return PMNET_OK;
+}
+
+int pmnet_density_post(const float* logits, const int32_t* tokens, const uint8_t* protein_mask,
+                       const uint8_t* cavity_mask, const float* taps3, float threshold, float* out, int32_t n,
+                       int32_t size, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!logits || !tokens || !protein_mask || !cavity_mask || !taps3 || !out) {
+    pmnet_set_error("pmnet_density_post: null argument");
+    return PMNET_EINVAL;
+  }
+  if (n <= 0 || size <= 0) {
+    pmnet_set_error("pmnet_density_post: bad shape");
+    return PMNET_EINVAL;
+  }
+  const int V = size * size * size;
+  dim3 grid((V + 255) / 256, n);
+  density_post_kernel<<<grid, 256, 0, stream>>>(logits, tokens, protein_mask, cavity_mask, taps3[0], taps3[1], taps3[2],
+                                                threshold, out, size);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    pmnet_set_error(cudaGetErrorString(e));
+    return PMNET_ECUDA;
+  }
+  return PMNET_OK;
+}
+
+}  // extern "C"

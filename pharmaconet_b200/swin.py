@@ -1,0 +1,119 @@
+"""3-D Swin Transformer V2 backbone of the reference network, written functionally on top of a state dict.
+
+Reference: src/pmnet/network/backbones/swinv2.py (WindowAttention :20-163, SwinTransformerBlock :166-311,
+PatchMerging :314-363, PatchEmbed :450-500, SwinTransformerV2.forward :626-644) with the fixed configuration of
+builder.py:15-24 (patch 2, dim 96, depths (2,6,2,2), heads (3,6,12,24), window 4). It is ~10 % of the forward FLOPs
+ and is made of plain GEMMs, LayerNorms and 64-token window attention, run here in fp32 through
+torch (cuBLAS) - the tensor-core work of this package is the convolution stack. Reference quirks kept: the cyclic
+shift rolls only the first two spatial axes (swinv2.py:277,296) while the stored attention mask covers three; the
+continuous position bias is 16*sigmoid(cpb_mlp(table)); logit scale clamped at log(100); res-post-norm.
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+DEPTHS = (2, 6, 2, 2)
+HEADS = (3, 6, 12, 24)
+WINDOW = 4
+EMBED = 96
+PATCH = 2
+
+
+def _window_partition(x: torch.Tensor, ws: int) -> torch.Tensor:
+    B, D, H, W, C = x.shape
+    x = x.view(B, D // ws, ws, H // ws, ws, W // ws, ws, C)
+    return x.permute(0, 1, 3, 5, 2, 4, 6, 7).reshape(-1, ws * ws * ws, C)
+
+
+def _window_reverse(win: torch.Tensor, ws: int, B: int, D: int, H: int, W: int) -> torch.Tensor:
+    x = win.view(B, D // ws, H // ws, W // ws, ws, ws, ws, -1)
+    return x.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(B, D, H, W, -1)
+
+
+class SwinV2Backbone:
+    def __init__(self, sd: dict[str, torch.Tensor], prefix: str = "embedding.backbone.", image_size: int = 64):
+        self.sd = sd
+        self.p = prefix
+        self.res0 = image_size // PATCH
+        self._bias_cache: dict[str, torch.Tensor] = {}
+
+    def _g(self, name: str) -> torch.Tensor:
+        return self.sd[self.p + name]
+
+    def _rel_bias(self, blk: str, heads: int, n: int) -> torch.Tensor:
+        """16 * sigmoid(cpb_mlp(relative_coords_table))[relative_position_index] -> [heads, n, n]; input independent."""
+        if blk not in self._bias_cache:
+            table = self._g(blk + "attn.relative_coords_table")
+            h = F.relu(F.linear(table, self._g(blk + "attn.cpb_mlp.0.weight"), self._g(blk + "attn.cpb_mlp.0.bias")))
+            t = F.linear(h, self._g(blk + "attn.cpb_mlp.2.weight")).view(-1, heads)
+            idx = self._g(blk + "attn.relative_position_index").view(-1)
+            bias = t[idx].view(n, n, heads).permute(2, 0, 1).contiguous()
+            self._bias_cache[blk] = 16.0 * torch.sigmoid(bias)
+        return self._bias_cache[blk]
+
+    def _attention(self, xw: torch.Tensor, blk: str, heads: int, mask: torch.Tensor | None) -> torch.Tensor:
+        Bw, N, C = xw.shape
+        qb, vb = self._g(blk + "attn.q_bias"), self._g(blk + "attn.v_bias")
+        qkv = F.linear(xw, self._g(blk + "attn.qkv.weight"), torch.cat((qb, torch.zeros_like(vb), vb)))
+        qkv = qkv.reshape(Bw, N, 3, heads, -1).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv[0], qkv[1], qkv[2]
+        attn = F.normalize(q, dim=-1) @ F.normalize(k, dim=-1).transpose(-2, -1)
+        scale = torch.clamp(self._g(blk + "attn.logit_scale"), max=math.log(1.0 / 0.01)).exp()
+        attn = attn * scale + self._rel_bias(blk, heads, N).unsqueeze(0)
+        if mask is not None:
+            nW = mask.shape[0]
+            attn = (attn.view(Bw // nW, nW, heads, N, N) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, N, N)
+        attn = torch.softmax(attn, dim=-1)
+        out = (attn @ v).transpose(1, 2).reshape(Bw, N, C)
+        return F.linear(out, self._g(blk + "attn.proj.weight"), self._g(blk + "attn.proj.bias"))
+
+    def _block(self, x: torch.Tensor, blk: str, res: int, heads: int, shift: int) -> torch.Tensor:
+        B, L, C = x.shape
+        ws = WINDOW
+        if res <= ws:  # swinv2.py:206-209
+            ws, shift = res, 0
+        h = x.view(B, res, res, res, C)
+        if shift > 0:
+            h = torch.roll(h, shifts=(-shift, -shift), dims=(1, 2))
+        mask = self.sd.get(self.p + blk + "attn_mask") if shift > 0 else None
+        aw = self._attention(_window_partition(h, ws), blk, heads, mask)
+        h = _window_reverse(aw, ws, B, res, res, res)
+        if shift > 0:
+            h = torch.roll(h, shifts=(shift, shift), dims=(1, 2))
+        h = h.reshape(B, L, C)
+        x = x + F.layer_norm(h, (C,), self._g(blk + "norm1.weight"), self._g(blk + "norm1.bias"))
+        m = F.linear(x, self._g(blk + "mlp.fc1.weight"), self._g(blk + "mlp.fc1.bias"))
+        m = F.linear(F.gelu(m), self._g(blk + "mlp.fc2.weight"), self._g(blk + "mlp.fc2.bias"))
+        return x + F.layer_norm(m, (C,), self._g(blk + "norm2.weight"), self._g(blk + "norm2.bias"))
+
+    def _merge(self, x: torch.Tensor, pre: str, res: int) -> torch.Tensor:
+        B, L, C = x.shape
+        x = x.view(B, res, res, res, C)
+        parts = [x[:, i::2, j::2, k::2, :] for k in (0, 1) for j in (0, 1) for i in (0, 1)]  # swinv2.py:346-354 order
+        x = torch.cat(parts, -1).reshape(B, -1, 8 * C)
+        x = F.linear(x, self._g(pre + "reduction.weight"))
+        return F.layer_norm(x, (2 * C,), self._g(pre + "norm.weight"), self._g(pre + "norm.bias"))
+
+    @torch.no_grad()
+    def forward(self, image: torch.Tensor) -> list[torch.Tensor]:
+        """image fp32 [B, 33, 64, 64, 64] -> [B,96,32^3], [B,192,16^3], [B,384,8^3], [B,768,4^3] (NCDHW fp32)."""
+        x = F.conv3d(image, self._g("patch_embed.proj.weight"), self._g("patch_embed.proj.bias"), stride=PATCH)
+        B, C = x.shape[0], x.shape[1]
+        x = x.flatten(2).transpose(1, 2)
+        x = F.layer_norm(x, (C,), self._g("patch_embed.norm.weight"), self._g("patch_embed.norm.bias"))
+        outs = []
+        res, dim = self.res0, EMBED
+        for li, (depth, heads) in enumerate(zip(DEPTHS, HEADS)):
+            for bi in range(depth):
+                x = self._block(x, f"layers.{li}.blocks.{bi}.", res, heads, 0 if bi % 2 == 0 else WINDOW // 2)
+            o = F.layer_norm(x, (dim,), self._g(f"norm{li}.weight"), self._g(f"norm{li}.bias"))
+            outs.append(o.view(B, res, res, res, dim).permute(0, 4, 1, 2, 3).contiguous())
+            if li < len(DEPTHS) - 1:
+                x = self._merge(x, f"layers.{li}.downsample.", res)
+                res //= 2
+                dim *= 2
+        return outs

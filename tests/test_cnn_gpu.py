@@ -1,0 +1,114 @@
+"""CNN forward (pharmaconet_b200.cnn.PharmacoNetModel) against golden vectors of the reference network run on CPU in
+fp32 (oracle/make_golden_cnn.py). The backbone is fp32 here too; everything after it runs on bf16 tensor-core
+operands with fp32 accumulation, so the tolerances are bf16-level and are written next to each check. Integer
+outputs (cavity masks, segmentation masks) are compared bit for bit and the flip count is bounded."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+from golden_util import GOLDEN
+
+from pharmaconet_b200 import cnn, cnn_weights
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    man = json.load(open(os.path.join(GOLDEN, "cnn_manifest.json")))
+    buf = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, "cnn_buffers.npz")).items()}
+    sd = cnn_weights.synth_state_dict(man, buf, 0)
+    model = cnn.PharmacoNetModel(sd, "cuda:0")
+    gold = np.load(os.path.join(GOLDEN, "cnn_golden.npz"))
+    g = torch.Generator().manual_seed(0)
+    image = torch.rand((1, 33, 64, 64, 64), generator=g)
+    tokens = torch.cat([torch.randint(0, 64, (200, 3), generator=g), torch.randint(0, 10, (200, 1), generator=g)], dim=1)
+    assert np.array_equal(tokens.numpy(), gold["tokens"])
+    feats = model.forward_feature(image.cuda())
+    return dict(model=model, gold=gold, image=image, tokens=tokens.long(), feats=feats)
+
+
+def _sample(t, n):
+    s = max(1, t.shape[-1] // n)
+    return t[0, :, ::s, ::s, ::s].float().cpu().numpy()
+
+
+def test_backbone_fp32(setup):
+    outs = setup["model"].backbone.forward(setup["image"].cuda())
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for i, t in enumerate(outs):
+        ref = setup["gold"][f"backbone{i}"]
+        err = np.abs(_sample(t, 4) - ref).max()
+        assert err <= 2e-3 * max(1.0, np.abs(ref).max()), (i, err)  # fp32 GEMM order / cuDNN patch-embed conv
+
+
+def test_forward_feature(setup):
+    feats = setup["feats"]
+    assert [tuple(f.shape) for f in feats] == [(1, 96, s, s, s) for s in (4, 8, 16, 32, 64)]
+    for i, f in enumerate(feats):
+        ref = setup["gold"][f"feat{i}"].astype(np.float32)
+        mine = _sample(f, 8)
+        scale = float(setup["gold"][f"feat{i}_absmean"])
+        rel_rms = np.sqrt(np.mean((mine - ref) ** 2)) / np.sqrt(np.mean(ref**2))
+        # each level stacks 2-9 bf16 convolutions: rms error a few bf16 ulps (2^-8), outliers < 10 % of the mean level
+        assert rel_rms <= 2e-2, (i, rel_rms)
+        assert np.abs(mine - ref).max() <= 0.15 * max(scale, 1e-3) + 0.05 * np.abs(ref).max(), (i, np.abs(mine - ref).max())
+
+
+def test_cavity_masks(setup):
+    narrow, wide = setup["model"].forward_cavity_extraction(setup["feats"][-1])
+    assert narrow.shape == (1, 1, 64, 64, 64) and wide.shape == (1, 1, 64, 64, 64)
+    for name, t in (("narrow", narrow), ("wide", wide)):
+        ref16 = setup["gold"][f"cavity_{name}_f16_s4"].astype(np.float32)
+        mine = t[0, 0, ::4, ::4, ::4].cpu().numpy()
+        assert np.sqrt(np.mean((mine - ref16) ** 2)) <= 3e-2 * np.sqrt(np.mean(ref16**2)) + 1e-2
+        bits = np.unpackbits(setup["gold"][f"cavity_{name}_bits"]).astype(bool)
+        mine_bits = (t[0, 0] > 0).reshape(-1).cpu().numpy()
+        flips = int((bits != mine_bits).sum())
+        # sigmoid(x) > 0.5 <=> x > 0 (module.py:232-233); voxels whose fp32 logit is within bf16 noise of 0 may flip
+        assert flips <= 0.003 * bits.size, (name, flips)
+        print(f"cavity {name}: {flips} of {bits.size} mask voxels differ from the fp32 reference")
+
+
+def test_token_prediction(setup):
+    scores, tfeat = setup["model"].forward_token_prediction(setup["feats"][-1], [setup["tokens"]])
+    ref_s, ref_f = setup["gold"]["token_scores"], setup["gold"]["token_features"]
+    assert scores[0].shape == (200,) and tfeat[0].shape == (200, 192)
+    assert np.abs(scores[0].cpu().numpy() - ref_s).max() <= 0.05 * max(1.0, np.abs(ref_s).max())
+    assert np.abs(tfeat[0].cpu().numpy() - ref_f).max() <= 0.05 * max(1.0, np.abs(ref_f).max())
+
+
+def test_segmentation(setup):
+    model, gold = setup["model"], setup["gold"]
+    _, tfeat = model.forward_token_prediction(setup["feats"][-1], [setup["tokens"]])
+    hot = setup["tokens"][:4]
+    seg = model.forward_segmentation(setup["feats"], [hot], [tfeat[0][:4]])[0][0]
+    assert seg.shape == (4, 64, 64, 64)
+    ref = gold["seg_f16_s4"].astype(np.float32)
+    mine = seg[:, ::4, ::4, ::4].cpu().numpy()
+    assert np.sqrt(np.mean((mine - ref) ** 2)) <= 4e-2 * np.sqrt(np.mean(ref**2)) + 2e-2
+    bits = np.unpackbits(gold["seg_bits"]).astype(bool)
+    flips = int((bits != (seg > 0).reshape(-1).cpu().numpy()).sum())
+    assert flips <= 0.005 * bits.size, flips
+    print(f"segmentation: {flips} of {bits.size} mask voxels differ from the fp32 reference")
+    # empty group and a short group keep the reference's shapes
+    empty = model.forward_segmentation(setup["feats"], [hot[:0]], [tfeat[0][:0]])[0][0]
+    assert empty.shape == (0, 64, 64, 64)
+    one = model.forward_segmentation(setup["feats"], [hot[:1]], [tfeat[0][:1]])[0][0]
+    assert one.shape == (1, 64, 64, 64)
+
+
+def test_density_post_matches_reference_exactly():
+    gold = np.load(os.path.join(GOLDEN, "cnn_golden.npz"))
+    gm = torch.Generator().manual_seed(1)
+    logits = torch.randn((4, 64, 64, 64), generator=gm) * 3.0 + 1.0
+    protein = torch.rand((64, 64, 64), generator=gm) < 0.8
+    cavity = torch.rand((1, 64, 64, 64), generator=gm) < 0.8
+    tokens = torch.from_numpy(gold["tokens"][:4])
+    out = cnn.density_post(logits.cuda(), tokens, protein, cavity, 0.5).reshape(-1).cpu()
+    nz = torch.nonzero(out).reshape(-1).numpy()
+    assert np.array_equal(nz, gold["post_nonzero_index"])  # the support of the maps is an integer output: exact
+    assert np.abs(out.numpy()[nz] - gold["post_nonzero_value"]).max() <= 2e-6
