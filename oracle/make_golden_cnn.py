@@ -106,5 +106,77 @@ def main():
     print("token score range", float(scores[0].min()), float(scores[0].max()))
 
 
+def main_pipeline():
+    """The reference's PharmacoNet.create_density_maps (module.py:215-309) + PharmacophoreModel.create, unmodified,
+    on a synthetic checkpoint and seeded protein data; tokens are drawn inside the reference's own cavity so that the
+    filter keeps a useful number of them."""
+    import pickle
+    import tempfile
+
+    ref_harness.import_reference()
+    import pmnet.module as ref_module
+    from pmnet.network import build_model
+    from pmnet.pharmacophore_model import PharmacophoreModel
+
+    manifest = json.load(open(os.path.join(GOLDEN, "cnn_manifest.json")))
+    buffers = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, "cnn_buffers.npz")).items()}
+    ckpt = cnn_weights.synth_checkpoint(manifest, buffers, SEED)
+    ref_module.OmegaConf.create = lambda cfg: type("Cfg", (), {"MODEL": {}})()  # the stubbed OmegaConf
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "model.tar")
+        torch.save(ckpt, path)
+        net = ref_module.PharmacoNet("cpu", verbose=False, molvoxel_library="numpy", weight_path=path)
+    g = torch.Generator().manual_seed(SEED)
+    image = torch.rand((33, 64, 64, 64), generator=g)
+    gm = torch.Generator().manual_seed(SEED + 2)
+    mask = torch.rand((64, 64, 64), generator=gm) < 0.8
+    with torch.no_grad():
+        feats = net.model.forward_feature(image.unsqueeze(0))
+        narrow, wide = net.model.forward_cavity_extraction(feats[-1])
+    # tokens: 120 inside the narrow cavity (margin > 0.3 in logit so that bf16 noise does not move them out),
+    # 40 inside the wide cavity, 40 anywhere
+    def pick(logit, n, margin):
+        idx = torch.nonzero(logit[0, 0] > margin)
+        sel = idx[torch.randperm(idx.shape[0], generator=gm)[:n]]
+        return sel
+    short_types = torch.tensor([0, 5, 6, 9])
+    long_types = torch.tensor([1, 2, 3, 4, 7, 8])
+    t_short = pick(narrow, 120, 0.3)
+    t_long = pick(wide, 40, 0.3)
+    t_any = torch.randint(0, 64, (40, 3), generator=gm)
+    tokens = torch.cat(
+        [
+            torch.cat([t_short, short_types[torch.randint(0, 4, (t_short.shape[0], 1), generator=gm)]], 1),
+            torch.cat([t_long, long_types[torch.randint(0, 6, (t_long.shape[0], 1), generator=gm)]], 1),
+            torch.cat([t_any, torch.randint(0, 10, (40, 1), generator=gm)], 1),
+        ]
+    ).long()
+    token_pos = (tokens[:, :3].float() - 31.5) * 0.5
+    infos = net.create_density_maps((image, mask, token_pos, tokens))
+    model = PharmacophoreModel.create("", (0.0, 0.0, 0.0), infos)
+    # which tokens were selected (the reference does not return indices: recover them from the positions)
+    sel = []
+    for info in infos:
+        d = (token_pos - torch.as_tensor(info["hotspot_position"]).float()).abs().sum(1)
+        cand = torch.nonzero(d < 1e-6).reshape(-1).tolist()
+        sel.append([c for c in cand if ref_module.C.INTERACTION_LIST[int(tokens[c, 3])] == info["nci_type"]][0])
+    out = dict(
+        tokens=tokens.numpy(),
+        selected_with_nonempty_map=np.asarray(sel, dtype=np.int64),
+        rel_scores=np.asarray([i["hotspot_score"] for i in infos], dtype=np.float64),
+        map_nonzero=np.asarray([int((i["point_map"] > 0).sum()) for i in infos], dtype=np.int64),
+        map_sum=np.asarray([float(i["point_map"].sum()) for i in infos], dtype=np.float64),
+        model_nodes=np.asarray(len(model.nodes)),
+        model_clusters=np.asarray(len(model.node_clusters)),
+    )
+    np.savez_compressed(os.path.join(GOLDEN, "cnn_pipeline_golden.npz"), **out)
+    print("pipeline: tokens", tokens.shape[0], "hotspots with maps", len(infos), "model nodes", len(model.nodes),
+          "clusters", len(model.node_clusters))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "pipeline":
+        main_pipeline()
+    else:
+        main()
+        main_pipeline()

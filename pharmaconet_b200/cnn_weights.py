@@ -61,3 +61,14 @@ def synth_state_dict(manifest: dict[str, list[int]], buffers: dict[str, torch.Te
 def buffer_name(key: str, shape) -> str:
     leaf = key.rsplit(".", 1)[-1]
     return leaf + "_" + "x".join(str(int(s)) for s in shape)
+
+
+def synth_checkpoint(manifest, buffers, seed: int = 0) -> dict:
+    """A stand-in for the reference's model.tar (module.py:82-93): synthetic weights + seeded score distributions."""
+    import numpy as np
+
+    from .constants import INTERACTION_LIST
+
+    rng = np.random.default_rng(seed + 17)
+    dists = {typ: {"focus": np.sort(rng.uniform(0.2, 1.0, size=2000)).tolist()} for typ in INTERACTION_LIST}
+    return {"config": {"MODEL": {}}, "model": synth_state_dict(manifest, buffers, seed), "score_distributions": dists}

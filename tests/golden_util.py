@@ -8,7 +8,9 @@ import numpy as np
 from pharmaconet_b200.packing import LigandBatch, PackedModel
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
+CASES = sorted(
+    os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(f).startswith("cnn_")
+)  # scoring cases; cnn_*.npz belong to tests/test_cnn_gpu.py
 
 
 def load_case(name):

@@ -112,3 +112,57 @@ def test_density_post_matches_reference_exactly():
     nz = torch.nonzero(out).reshape(-1).numpy()
     assert np.array_equal(nz, gold["post_nonzero_index"])  # the support of the maps is an integer output: exact
     assert np.abs(out.numpy()[nz] - gold["post_nonzero_value"]).max() <= 2e-6
+
+
+def test_modeling_pipeline_against_reference_pharmaconet():
+    """PharmacoNet.create_density_maps + PharmacophoreModel.create end to end against the reference's own module.py
+    run on CPU (oracle/make_golden_cnn.py pipeline): selected hotspot indices are an integer output."""
+    from pharmaconet_b200.module import PharmacoNet
+
+    gold = np.load(os.path.join(GOLDEN, "cnn_pipeline_golden.npz"))
+    man = json.load(open(os.path.join(GOLDEN, "cnn_manifest.json")))
+    buf = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, "cnn_buffers.npz")).items()}
+    net = PharmacoNet("cuda:0", verbose=False, checkpoint=cnn_weights.synth_checkpoint(man, buf, 0))
+    g = torch.Generator().manual_seed(0)
+    image = torch.rand((33, 64, 64, 64), generator=g)
+    gm = torch.Generator().manual_seed(2)
+    mask = torch.rand((64, 64, 64), generator=gm) < 0.8
+    tokens = torch.from_numpy(gold["tokens"]).long()
+    token_pos = (tokens[:, :3].float() - 31.5) * 0.5
+    infos = net.create_density_maps((image, mask, token_pos, tokens))
+    # recover the selected token indices from positions + types
+    sel = []
+    for info in infos:
+        d = (token_pos - torch.as_tensor(info["hotspot_position"]).float()).abs().sum(1)
+        cand = torch.nonzero(d < 1e-6).reshape(-1).tolist()
+        sel.append([c for c in cand if net_type(tokens[c, 3]) == info["nci_type"]][0])
+    ref_sel = gold["selected_with_nonempty_map"].tolist()
+    common = sorted(set(sel) & set(ref_sel))
+    print(f"hotspots: reference {len(ref_sel)}, here {len(sel)}, common {len(common)}")
+    # bf16 features move token scores by ~1e-2: a token whose relative score sits on its threshold may flip
+    assert len(common) >= 0.9 * len(ref_sel) and len(sel) <= 1.1 * len(ref_sel) + 1
+    nz_ref = dict(zip(ref_sel, gold["map_nonzero"].tolist()))
+    nz = {s: int((i["point_map"] > 0).sum()) for s, i in zip(sel, infos)}
+    rel = [abs(nz[c] - nz_ref[c]) / max(nz_ref[c], 1) for c in common]
+    assert np.median(rel) <= 0.05, np.median(rel)
+    rs_ref = dict(zip(ref_sel, gold["rel_scores"].tolist()))
+    rs = {s: i["hotspot_score"] for s, i in zip(sel, infos)}
+    assert max(abs(rs[c] - rs_ref[c]) for c in common) <= 0.05
+    model = net.create_model((image, mask, token_pos, tokens))
+    assert abs(len(model.nodes) - int(gold["model_nodes"])) <= 0.15 * int(gold["model_nodes"])
+    # run_extraction: same selection rule without the mask head
+    feats, hinfos = net.run_extraction((image, mask, token_pos, tokens))
+    assert len(feats) == 5 and feats[-1].shape == (1, 96, 64, 64, 64)
+    assert len(hinfos) >= len(infos) and all(h["hotspot_feature"].shape == (192,) for h in hinfos)
+    # and the model scores ligands on the same device (config 5 in miniature)
+    from pharmaconet_b200 import synthetic
+    from pharmaconet_b200.packing import LigandBatch
+
+    scores = model.scoring_batch(LigandBatch.from_typed(synthetic.make_ligands(64, 8, seed=5)), device="cuda:0")
+    assert scores.shape == (64,) and np.all(np.isfinite(scores))
+
+
+def net_type(t):
+    from pharmaconet_b200.constants import INTERACTION_LIST
+
+    return INTERACTION_LIST[int(t)]
