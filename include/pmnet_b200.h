@@ -165,10 +165,10 @@ int pmnet_lateral_c96(const void* x, int32_t x_is_c8, int32_t c_in, const float*
  *   out[j] = act(scale * (S + u[j] + [voxel in pvox] pvec[j]) + bias) + nearest_upsample(up[j])
  *   s_c8 : bf16 c8 [12][D][H][W][8] shared by the group (the lateral conv of the pocket's feature map, or the feature
  *          map itself at the top level where the lateral is the identity: then scale = bias = NULL, relu = 0)
- *   u, pvec : fp32 [nbox][96]; pvox int32 [n_pvox] flat voxel ids of ALL token voxels of the group (every box gets
- *          its own pvec at all of them - the reference's broadcasting)
+ *   u, pvec : fp32 [nbox][96]; pvox int32 [nbox][4] flat voxel ids (-1 = unused) of the token voxels of the box's
+ *          group of 4 (every box gets its own pvec at all of them - the reference's broadcasting)
  *   up_c8 : optional bf16 c8 [nbox][12][D/2][H/2][W/2][8]; out_c8 bf16 c8 [nbox][12][D][H][W][8] */
-int pmnet_box_combine_c96(const void* s_c8, const float* u, const float* pvec, const int32_t* pvox, int32_t n_pvox,
+int pmnet_box_combine_c96(const void* s_c8, const float* u, const float* pvec, const int32_t* pvox,
                           const float* scale, const float* bias, int32_t relu, const void* up_c8, void* out_c8,
                           int32_t nbox, int32_t D, int32_t H, int32_t W, void* stream);
 

@@ -92,7 +92,7 @@ def lib() -> C.CDLL:
     ]  # fmt: skip
     L.pmnet_box_combine_c96.restype = C.c_int
     L.pmnet_box_combine_c96.argtypes = [
-        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
         C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
     ]  # fmt: skip
     L.pmnet_density_post.restype = C.c_int

@@ -104,7 +104,7 @@ class PharmacoNetModel:
         _, D, H, W, _ = s_c8.shape
         out = torch.empty((nbox, 12, D, H, W, 8), dtype=torch.bfloat16, device=self.device)
         rc = self._L.pmnet_box_combine_c96(
-            s_c8.data_ptr(), u.data_ptr(), pvec.data_ptr(), pvox.data_ptr(), pvox.numel(),
+            s_c8.data_ptr(), u.data_ptr(), pvec.data_ptr(), pvox.data_ptr(),
             layer.scale.data_ptr() if layer is not None else None, layer.bias.data_ptr() if layer is not None else None,
             int(layer is not None), up_c8.data_ptr() if up_c8 is not None else None, out.data_ptr(),
             nbox, D, H, W, _stream(self.device),
@@ -208,7 +208,14 @@ class PharmacoNetModel:
         return cache[b]
 
     @torch.no_grad()
-    def forward_segmentation(self, multi_scale_features, box_tokens_list, box_token_features_list, return_aux=False):
+    def forward_segmentation(
+        self, multi_scale_features, box_tokens_list, box_token_features_list, return_aux=False, group_size=None
+    ):
+        """mask_head.py:38-80. The reference adds every box's point feature at the token voxels of ALL boxes passed
+        in the same call (mask_head.py:190-194) and its caller passes groups of 4 (module.py:261-272). `group_size`
+        reproduces that grouping inside ONE call over all hotspots of a pocket (boxes i..i+group_size-1 form a
+        group), which lets the convolutions run at full batch; None = the whole list is one group, exactly like the
+        reference called with that list."""
         if return_aux:
             raise NotImplementedError("auxiliary multi-scale masks are a training-time output of the reference")
         sd = self.sd
@@ -220,29 +227,41 @@ class PharmacoNetModel:
             if nbox == 0:
                 out_masks.append(torch.empty((0, size, size, size), dtype=torch.float32, device=self.device))
                 continue
+            gs = nbox if group_size is None else int(group_size)
+            if gs > 4:
+                raise NotImplementedError("groups of more than 4 boxes are not supported by the combine kernel")
             tfeat = tfeat.to(self.device, torch.float32)
             shared = self._shared_laterals(multi_scale_features, b)
-            fpn = None
-            for level in (4, 3, 2, 1, 0):
-                s = shared[level]
-                D = s.shape[1]
-                div = size // D
-                vox = ((tokens[:, 0] // div) * D + tokens[:, 1] // div) * D + tokens[:, 2] // div
-                pvox = torch.unique(vox).to(torch.int32)
-                bg = F.linear(tfeat, sd[f"mask_head.background_mlp_list.{level}.weight"], sd[f"mask_head.background_mlp_list.{level}.bias"])
-                pt = F.linear(tfeat, sd[f"mask_head.point_mlp_list.{level}.weight"], sd[f"mask_head.point_mlp_list.{level}.bias"])
-                lat = self.mask_lateral[level]
-                if lat is not None:  # push the per-box vectors through the (linear) 1x1 conv
-                    wl = lat.weight.reshape(96, 96).float()
-                    bg, pt = bg @ wl.t(), pt @ wl.t()
-                fpn = self._combine(s, bg.contiguous(), pt.contiguous(), pvox, lat, fpn)
-                convs = self.mask_convs[level]
-                for i, layer in enumerate(convs):
-                    if level == 0 and i == len(convs) - 1:
-                        _, logits = self._k3(fpn, layer, head=(self.mask_logit_w, self.mask_logit_b), store_out=False)
-                    else:
-                        fpn = self._k3(fpn, layer)[0]
-            out_masks.append(logits)
+            member = (torch.arange(nbox, device=self.device) // gs) * gs  # first box of each box's group
+            pieces = []
+            for lo in range(0, nbox, 48):  # bound the per-call activation memory (48 boxes x 50 MB at 64^3)
+                hi = min(nbox, lo + 48)
+                fpn = None
+                for level in (4, 3, 2, 1, 0):
+                    s = shared[level]
+                    D = s.shape[1]
+                    div = size // D
+                    vox = ((tokens[:, 0] // div) * D + tokens[:, 1] // div) * D + tokens[:, 2] // div
+                    pvox = torch.full((hi - lo, 4), -1, dtype=torch.int32, device=self.device)
+                    for k in range(gs):
+                        src = member[lo:hi] + k
+                        ok = src < nbox
+                        pvox[ok, k] = vox[src[ok]].to(torch.int32)
+                    bg = F.linear(tfeat[lo:hi], sd[f"mask_head.background_mlp_list.{level}.weight"], sd[f"mask_head.background_mlp_list.{level}.bias"])
+                    pt = F.linear(tfeat[lo:hi], sd[f"mask_head.point_mlp_list.{level}.weight"], sd[f"mask_head.point_mlp_list.{level}.bias"])
+                    lat = self.mask_lateral[level]
+                    if lat is not None:  # push the per-box vectors through the (linear) 1x1 conv
+                        wl = lat.weight.reshape(96, 96).float()
+                        bg, pt = bg @ wl.t(), pt @ wl.t()
+                    fpn = self._combine(s, bg.contiguous(), pt.contiguous(), pvox, lat, fpn)
+                    convs = self.mask_convs[level]
+                    for i, layer in enumerate(convs):
+                        if level == 0 and i == len(convs) - 1:
+                            _, logits = self._k3(fpn, layer, head=(self.mask_logit_w, self.mask_logit_b), store_out=False)
+                        else:
+                            fpn = self._k3(fpn, layer)[0]
+                pieces.append(logits)
+            out_masks.append(pieces[0] if len(pieces) == 1 else torch.cat(pieces, 0))
         return out_masks, None
 
 

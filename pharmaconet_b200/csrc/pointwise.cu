@@ -103,10 +103,11 @@ __global__ void __launch_bounds__(128) lateral_kernel(const void* __restrict__ x
 }
 
 // ------------------------------------------------------------------ per-box combine
-// out[j] = act(scale * (S + u_j + [v in P] p_j) + bias) + up_j ; thread = (voxel, chunk), loops over boxes.
+// out[j] = act(scale * (S + u_j + [v in P_j] p_j) + bias) + up_j ; thread = (voxel, chunk), loops over boxes.
+// P_j = up to 4 voxel ids per box (-1 padded): the token voxels of the box's group of 4 (mask_head.py:190-194).
 __global__ void __launch_bounds__(256) box_combine_kernel(const uint4* __restrict__ S, const float* __restrict__ u,
-                                                          const float* __restrict__ pvec, const int* __restrict__ pvox,
-                                                          int n_pvox, const float* __restrict__ scale,
+                                                          const float* __restrict__ pvec, const int4* __restrict__ pvox,
+                                                          const float* __restrict__ scale,
                                                           const float* __restrict__ bias, int relu,
                                                           const uint4* __restrict__ up, uint4* __restrict__ out,
                                                           int nbox, int D, int H, int W) {
@@ -116,19 +117,25 @@ __global__ void __launch_bounds__(256) box_combine_kernel(const uint4* __restric
   const int chunk = (int)(idx / V), v = (int)(idx % V);
   float s[8];
   unpack8(__ldg(S + idx), s);
-  bool at_point = false;
-  for (int i = 0; i < n_pvox; ++i) at_point |= (pvox[i] == v);
+  float sc[8], bi[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = scale ? __ldg(scale + chunk * 8 + k) : 1.0f;
+    bi[k] = scale ? __ldg(bias + chunk * 8 + k) : 0.0f;
+  }
   const int w = v % W, h = (v / W) % H, d = v / (W * H);
   const int Vu = (D / 2) * (H / 2) * (W / 2);
   const int vu = ((d >> 1) * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1);
   for (int j = 0; j < nbox; ++j) {
+    const int4 pv = __ldg(pvox + j);
+    const bool at_point = (pv.x == v) | (pv.y == v) | (pv.z == v) | (pv.w == v);
     float y[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = chunk * 8 + k;
       float t = s[k] + __ldg(u + j * 96 + c);
       if (at_point) t += __ldg(pvec + j * 96 + c);
-      if (scale) t = fmaf(t, __ldg(scale + c), __ldg(bias + c));
+      t = fmaf(t, sc[k], bi[k]);
       if (relu) t = fmaxf(t, 0.0f);
       y[k] = t;
     }
@@ -236,21 +243,22 @@ int pmnet_lateral_c96(const void* x, int32_t x_is_c8, int32_t c_in, const float*
   return PMNET_OK;
 }
 
-int pmnet_box_combine_c96(const void* s_c8, const float* u, const float* pvec, const int32_t* pvox, int32_t n_pvox,
+int pmnet_box_combine_c96(const void* s_c8, const float* u, const float* pvec, const int32_t* pvox,
                           const float* scale, const float* bias, int32_t relu, const void* up_c8, void* out_c8,
                           int32_t nbox, int32_t D, int32_t H, int32_t W, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!s_c8 || !u || !out_c8 || (n_pvox > 0 && (!pvec || !pvox)) || (scale && !bias)) {
+  if (!s_c8 || !u || !out_c8 || !pvec || !pvox || (scale && !bias)) {
     pmnet_set_error("pmnet_box_combine_c96: null argument");
     return PMNET_EINVAL;
   }
-  if (nbox <= 0 || D <= 0 || H <= 0 || W <= 0 || n_pvox < 0 || (up_c8 && ((D | H | W) & 1))) {
+  if (nbox <= 0 || D <= 0 || H <= 0 || W <= 0 || (up_c8 && ((D | H | W) & 1))) {
     pmnet_set_error("pmnet_box_combine_c96: bad shape");
     return PMNET_EINVAL;
   }
   const size_t total = (size_t)12 * D * H * W;
   box_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-      (const uint4*)s_c8, u, pvec, pvox, n_pvox, scale, bias, relu, (const uint4*)up_c8, (uint4*)out_c8, nbox, D, H, W);
+      (const uint4*)s_c8, u, pvec, (const int4*)pvox, scale, bias, relu, (const uint4*)up_c8, (uint4*)out_c8, nbox, D, H,
+      W);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     pmnet_set_error(cudaGetErrorString(e));

@@ -217,9 +217,11 @@ class PharmacoNet:
         r = self._features_and_hotspots(protein_data)
         hotspots, feats = r["hotspots"], r["feats"]
         logits = []
-        for i in range(0, hotspots.shape[0], SEGMENTATION_GROUP):
-            sl = slice(i, i + SEGMENTATION_GROUP)
-            logits.append(self.model.forward_segmentation(feats, [hotspots[sl]], [r["features"][sl]])[0][0])
+        if hotspots.shape[0] > 0:
+            # all hotspots in one call; the reference's groups of 4 (module.py:261-272) are reproduced inside
+            logits.append(
+                self.model.forward_segmentation(feats, [hotspots], [r["features"]], group_size=SEGMENTATION_GROUP)[0][0]
+            )
         infos: list[HotspotInfo] = []
         if logits:
             maps = cnn.density_post(torch.cat(logits, 0), hotspots, r["mask"], r["narrow"][0], self.box_threshold)

@@ -40,6 +40,19 @@ class SwinV2Backbone:
         self.p = prefix
         self.res0 = image_size // PATCH
         self._bias_cache: dict[str, torch.Tensor] = {}
+        # "fp32" (default, parity with the reference's fp32 GEMMs) or "bf16" (GEMM operands in bf16, fp32 accumulate,
+        # LayerNorm / softmax / residuals in fp32) for throughput runs
+        self.precision = "fp32"
+        self._w16: dict[str, torch.Tensor] = {}
+
+    def _lin(self, x: torch.Tensor, wname: str, bias: torch.Tensor | None = None) -> torch.Tensor:
+        if self.precision == "bf16":
+            w = self._w16.get(wname)
+            if w is None:
+                w = self._w16[wname] = self._g(wname).to(torch.bfloat16)
+            y = F.linear(x.to(torch.bfloat16), w).float()
+            return y if bias is None else y + bias
+        return F.linear(x, self._g(wname), bias)
 
     def _g(self, name: str) -> torch.Tensor:
         return self.sd[self.p + name]
@@ -58,7 +71,7 @@ class SwinV2Backbone:
     def _attention(self, xw: torch.Tensor, blk: str, heads: int, mask: torch.Tensor | None) -> torch.Tensor:
         Bw, N, C = xw.shape
         qb, vb = self._g(blk + "attn.q_bias"), self._g(blk + "attn.v_bias")
-        qkv = F.linear(xw, self._g(blk + "attn.qkv.weight"), torch.cat((qb, torch.zeros_like(vb), vb)))
+        qkv = self._lin(xw, blk + "attn.qkv.weight", torch.cat((qb, torch.zeros_like(vb), vb)))
         qkv = qkv.reshape(Bw, N, 3, heads, -1).permute(2, 0, 3, 1, 4)
         q, k, v = qkv[0], qkv[1], qkv[2]
         attn = F.normalize(q, dim=-1) @ F.normalize(k, dim=-1).transpose(-2, -1)
@@ -69,7 +82,7 @@ class SwinV2Backbone:
             attn = (attn.view(Bw // nW, nW, heads, N, N) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, N, N)
         attn = torch.softmax(attn, dim=-1)
         out = (attn @ v).transpose(1, 2).reshape(Bw, N, C)
-        return F.linear(out, self._g(blk + "attn.proj.weight"), self._g(blk + "attn.proj.bias"))
+        return self._lin(out, blk + "attn.proj.weight", self._g(blk + "attn.proj.bias"))
 
     def _block(self, x: torch.Tensor, blk: str, res: int, heads: int, shift: int) -> torch.Tensor:
         B, L, C = x.shape
@@ -86,8 +99,8 @@ class SwinV2Backbone:
             h = torch.roll(h, shifts=(shift, shift), dims=(1, 2))
         h = h.reshape(B, L, C)
         x = x + F.layer_norm(h, (C,), self._g(blk + "norm1.weight"), self._g(blk + "norm1.bias"))
-        m = F.linear(x, self._g(blk + "mlp.fc1.weight"), self._g(blk + "mlp.fc1.bias"))
-        m = F.linear(F.gelu(m), self._g(blk + "mlp.fc2.weight"), self._g(blk + "mlp.fc2.bias"))
+        m = self._lin(x, blk + "mlp.fc1.weight", self._g(blk + "mlp.fc1.bias"))
+        m = self._lin(F.gelu(m), blk + "mlp.fc2.weight", self._g(blk + "mlp.fc2.bias"))
         return x + F.layer_norm(m, (C,), self._g(blk + "norm2.weight"), self._g(blk + "norm2.bias"))
 
     def _merge(self, x: torch.Tensor, pre: str, res: int) -> torch.Tensor:
@@ -95,7 +108,7 @@ class SwinV2Backbone:
         x = x.view(B, res, res, res, C)
         parts = [x[:, i::2, j::2, k::2, :] for k in (0, 1) for j in (0, 1) for i in (0, 1)]  # swinv2.py:346-354 order
         x = torch.cat(parts, -1).reshape(B, -1, 8 * C)
-        x = F.linear(x, self._g(pre + "reduction.weight"))
+        x = self._lin(x, pre + "reduction.weight")
         return F.layer_norm(x, (2 * C,), self._g(pre + "norm.weight"), self._g(pre + "norm.bias"))
 
     @torch.no_grad()
