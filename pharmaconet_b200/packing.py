@@ -296,3 +296,16 @@ class LigandBatch:
             coord_off=np.asarray(coord_off, dtype=np.int64),
             coords=np.concatenate(chunks) if chunks else np.zeros(0, np.float32),
         )
+
+
+def save_library(path, batch: LigandBatch, names: Sequence[str] | None = None) -> None:
+    """Packed library on disk (.npz): the LigandBatch arrays + optional ligand names (one per ligand)."""
+    extra = {} if names is None else {"names": np.asarray(list(names))}
+    np.savez(path, **batch.arrays(), **extra)
+
+
+def load_library(path) -> tuple[LigandBatch, list[str]]:
+    z = np.load(path, allow_pickle=False)
+    batch = LigandBatch.from_arrays({k: z[k] for k in LigandBatch.__dataclass_fields__})
+    names = [str(n) for n in z["names"]] if "names" in z.files else [f"ligand_{i}" for i in range(batch.num_ligands)]
+    return batch, names

@@ -1,0 +1,73 @@
+"""Functional-group typing rules on hand-made atom tables (no toolkit needed) and the failure mode without OpenBabel."""
+
+import pytest
+
+from pharmaconet_b200 import ligand_typing as lt
+from pharmaconet_b200.ligand import TypedLigand, build_topology
+
+
+def _table(z, bonds, hyb=None, acc=(), don=(), rings=()):
+    n = len(z)
+    nb = [[] for _ in range(n)]
+    for a, b in bonds:
+        nb[a].append(b)
+        nb[b].append(a)
+    return lt.AtomTable(
+        atomic_nums=list(z),
+        neighbors=nb,
+        explicit_degree=[len(x) for x in nb],
+        heavy_degree=[sum(1 for j in x if z[j] != 1) for x in nb],
+        hyb=list(hyb) if hyb else [3] * n,
+        is_acceptor=[i in acc for i in range(n)],
+        is_donor=[i in don for i in range(n)],
+        aromatic_rings=list(rings),
+    )
+
+
+def test_acetate_like():
+    # CH3-C(=O)O-: methyl carbon hydrophobic, carboxylate anion centred on the two oxygens, both oxygens acceptors
+    t = _table([6, 6, 8, 8], [(0, 1), (1, 2), (1, 3)], acc=(2, 3))
+    ph = lt.type_atoms(t)
+    assert ("Hydrophobic", 0, 0) in ph and ("Anion", (1, 2, 3), (2, 3)) in ph
+    assert [p for p in ph if p[0] == "HBond_acceptor"] == [("HBond_acceptor", 2, 2), ("HBond_acceptor", 3, 3)]
+    assert not [p for p in ph if p[0] in ("Cation", "Aromatic", "Halogen")]
+
+
+def test_amines_rings_halogens_order():
+    # chlorobenzene with a para trimethyl-amine: ring 0-5, Cl 6 on C0, N 7 on C3 with methyls 8, 9
+    bonds = [(i, (i + 1) % 6) for i in range(6)] + [(0, 6), (3, 7), (7, 8), (7, 9)]
+    t = _table([6] * 6 + [17, 7, 6, 6], bonds, acc=(7,), rings=[(5, 4, 3, 2, 1, 0)])
+    ph = lt.type_atoms(t)
+    kinds = [p[0] for p in ph]
+    assert kinds == sorted(kinds, key=["Hydrophobic", "Aromatic", "Cation", "Anion", "HBond_donor", "HBond_acceptor", "Halogen"].index)
+    assert ("Aromatic", (0, 1, 2, 3, 4, 5), (0, 1, 2, 3, 4, 5)) in ph
+    assert ("Cation", 7, 7) in ph and ("Halogen", 6, 6) in ph and ("HBond_acceptor", 7, 7) in ph
+    # ring carbons bonded to Cl / N are not hydrophobic; the other four are; the N-methyls are not (N neighbour)
+    assert [p[1] for p in ph if p[0] == "Hydrophobic"] == [1, 2, 4, 5]
+    # and the typed list feeds the graph builder: hydrophobic ring carbons join the aromatic cluster
+    top = build_topology(TypedLigand(t.atomic_nums, t.neighbors, ph, None))
+    kinds = sorted(c.kind for c in top.clusters)
+    assert kinds == ["Aromatic", "Cation", "Halogen"]
+
+
+def test_guanidine_phosphate_sulfonate():
+    # guanidine C(N)(N)N with one terminal N
+    t = _table([6, 7, 7, 7, 6], [(0, 1), (0, 2), (0, 3), (3, 4)])
+    assert ("Cation", (0, 1, 2, 3), 0) in lt.type_atoms(t)
+    # phosphate P(O)(O)(O)O-C
+    t = _table([15, 8, 8, 8, 8, 6], [(0, 1), (0, 2), (0, 3), (0, 4), (4, 5)])
+    assert ("Anion", (0, 1, 2, 3, 4), 0) in lt.type_atoms(t)
+    # sulfonic acid C-S(O)(O)O : only the oxygens join the atom key
+    t = _table([16, 8, 8, 8, 6], [(0, 1), (0, 2), (0, 3), (0, 4)])
+    assert ("Anion", (0, 1, 2, 3), 0) in lt.type_atoms(t)
+    # halogens never count as acceptors even when the toolkit flags them
+    t = _table([6, 9], [(0, 1)], acc=(1,))
+    assert not [p for p in lt.type_atoms(t) if p[0] == "HBond_acceptor"]
+
+
+def test_file_entry_points_fail_loudly_without_openbabel():
+    try:
+        import openbabel  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="OpenBabel"):
+            lt.typed_ligand_from_file("x.sdf")

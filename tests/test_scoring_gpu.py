@@ -157,3 +157,31 @@ def test_streamed_screening_reruns_overflow():
     assert rel_err(res.scores, c["ref"]).max() <= REL_TOL
     order = np.lexsort((np.arange(len(c["ref"])), -res.scores.astype(np.float64)))[:8]
     assert np.array_equal(res.topk_ids.cpu().numpy(), order)
+
+
+def test_screening_cli_on_packed_library(tmp_path):
+    import os
+    import subprocess
+    import sys
+
+    from golden_util import GOLDEN
+
+    from pharmaconet_b200.packing import save_library
+
+    c = load_case("syn0_c8")
+    names = [f"lig_{i:04d}.sdf" for i in range(c["batch"].num_ligands)]
+    save_library(tmp_path / "lib.npz", c["batch"], names)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "out.csv"
+    subprocess.run(
+        [sys.executable, os.path.join(root, "screening.py"), "-p", os.path.join(GOLDEN, "model_syn0.pm"),
+         "-d", str(tmp_path / "lib.npz"), "-o", str(out)],
+        check=True, cwd=root, timeout=300,
+    )  # fmt: skip
+    lines = out.read_text().splitlines()
+    assert lines[0] == "path,score" and len(lines) == 1 + len(names)
+    got = {ln.split(",")[0]: float(ln.split(",")[1]) for ln in lines[1:]}
+    vals = [float(ln.split(",")[1]) for ln in lines[1:]]
+    assert vals == sorted(vals, reverse=True)  # screening.py:70 sorts by score, descending
+    ref = dict(zip(names, c["ref"]))
+    assert max(abs(got[n] - ref[n]) / max(abs(ref[n]), 1e-12) for n in names) <= REL_TOL
