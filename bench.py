@@ -141,6 +141,49 @@ def workload_config(args, world):
     }
 
 
+def conv_leg(dev, batch: int = 8, iters: int = 10):
+    """Secondary measurement: the 96->96 3x3x3 convolution (+BN+ReLU) that is ~90 % of the CNN forward FLOPs
+    (BASELINE configs[3] shape: 64^3 grids), against the measured bf16 tensor peak."""
+    import torch
+
+    from pharmaconet_b200 import conv
+
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = conv.to_c8(torch.randn((batch, 96, 64, 64, 64), generator=g, device=dev))
+    w = conv.pack_weights_k3(torch.randn((96, 96, 3, 3, 3), generator=g, device=dev) * 0.03)
+    scale = torch.rand(96, generator=g, device=dev) + 0.5
+    bias = torch.randn(96, generator=g, device=dev) * 0.2
+    for _ in range(3):
+        conv.conv3d_k3_c96(x, w, scale, bias, True)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        conv.conv3d_k3_c96(x, w, scale, bias, True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    flop = 2.0 * batch * 64**3 * 96 * 96 * 27
+    peak, src = 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            peak, src = float(json.load(f)["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    prof_path = os.path.join(ROOT, "profiles", "conv3d_r01_ncu_full.json")
+    traffic = None
+    if os.path.exists(prof_path):
+        with open(prof_path) as f:
+            m = json.load(f)["metrics"]
+        unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        traffic = sum(float(m[k][0]) * unit[m[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    return {
+        "bound": "tensor", "achieved": flop / ms / 1e9, "peak": peak, "unit": "TFLOP/s", "frac": flop / ms / 1e9 / peak,
+        "traffic": traffic, "kernel": "conv3d_k3_c96_kernel", "kernel_ms_avg": ms, "flop_per_launch": flop,
+        "workload": f"{batch} x 96ch x 64^3 -> 96ch, 3x3x3, fused BN+ReLU, bf16 operands / fp32 accumulate",
+        "peak_source": src,
+    }  # fmt: skip
+
+
 def host_prefix(dev_lib, n):
     """First n ligands of a device library as a host LigandBatch (for the CPU port)."""
     import numpy as np
@@ -339,6 +382,14 @@ def main():
         rel = np.abs(g - ref_scores) / np.maximum(np.abs(ref_scores), 1e-12)
         parity = {"checked_ligands": int(done), "max_rel_err_vs_cpu_port": float(rel.max()), "tolerance": 1e-5}
 
+    # ---------------------------------------------------------------- leg 4: the CNN's dominant kernel (tensor roofline)
+    conv_roofline = None
+    if rank == 0:
+        try:
+            conv_roofline = conv_leg(dev)
+        except Exception as e:  # noqa: BLE001 - the headline metric must still be printed
+            conv_roofline = {"error": repr(e)}
+
     if rank == 0:
         peak, peak_src = load_peaks()
         achieved = alg_bytes / (kernel_ms_avg * 1e-3) / 1e9
@@ -359,6 +410,7 @@ def main():
                 "note": "the path is instruction-issue bound, not HBM bound (DESIGN.md section 5): the HBM fraction "
                         "is reported because BASELINE.json asks for it",
             },
+            "cnn_conv3d_roofline": conv_roofline,
             "cpu_baseline": cpu_baseline, "parity": parity, "clocks": clocks,
             "top1": {"id": int(top_ids[0]), "score": float(res.topk_scores[0].item())},
         }  # fmt: skip
