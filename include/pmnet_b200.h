@@ -58,7 +58,7 @@ enum {
   PMNET_LIG_UNSUPPORTED = 3 /* more conformers than PMNET_MAX_CONFORMERS */
 };
 
-#define PMNET_MAX_CONFORMERS 32   /* one warp lane per conformer */
+#define PMNET_MAX_CONFORMERS 128  /* one warp lane per conformer, up to 4 conformers per lane */
 #define PMNET_MAX_DEPTH 20        /* graph_match.py:88 */
 #define PMNET_MIN_MATCHES 5       /* tree.py:98 */
 
@@ -91,7 +91,7 @@ typedef struct PmLigandBatch {
   const int32_t* cluster_node_off; /* [total clusters + 1] */
   const uint8_t* cluster_nodes;    /* ligand-local node ids, high-priority node first (ligand.py:387-395) */
   const uint8_t* node_type_mask;   /* [total nodes] 7-bit mask of LigandNode.types */
-  const int32_t* n_conf;           /* [n] conformers per ligand, 1..PMNET_MAX_CONFORMERS */
+  const int32_t* n_conf;           /* [n] conformers per ligand, 1..PMNET_MAX_CONFORMERS (see PmScoreConfig) */
   const int64_t* coord_off;        /* [n+1] in floats */
   const float* coords;             /* fp32 node coordinates (LigandNode.positions, ligand.py:293-301) */
   /* A chunk of a larger library can be passed without re-basing its CSR offsets: the values stored in the
@@ -108,8 +108,9 @@ typedef struct PmLigandBatch {
 typedef struct PmScoreConfig {
   int32_t warps_per_block;   /* default 8 */
   int32_t blocks;            /* default: 2 x SM count */
-  int32_t scratch_rows;      /* per-warp pair-table capacity in 128 B rows; default 8192 */
-  int32_t reserved;
+  int32_t scratch_rows;      /* per-warp pair-table capacity in rows; default 8192 */
+  int32_t max_conformers;    /* largest n_conf in the batch (default 32): selects 1, 2 or 4 conformers per lane;
+                                ligands with more conformers than the launch was sized for get PMNET_LIG_UNSUPPORTED */
 } PmScoreConfig;
 
 int pmnet_abi_version(void);
@@ -122,7 +123,8 @@ size_t pmnet_score_workspace_bytes(int32_t n_model_nodes, int32_t n_model_cluste
  *   model, batch : HOST structs holding DEVICE array pointers
  *   weights      : HOST, 7 floats in PMNET_* type order (graph_match.py:32-40, 82-84)
  *   out_scores   : [n_ligands] fp32, mean over conformers of the best leaf score (graph_match.py:103-109)
- *   out_conf_scores : optional [n_ligands * 32] per-conformer best leaf score (lane-major), or NULL
+ *   out_conf_scores : optional [n_ligands * S] per-conformer best leaf score, S = 32 / 64 / 128 for max_conformers
+ *                     <= 32 / 64 / 128, or NULL
  *   out_status   : [n_ligands] PMNET_LIG_* code
  *   out_stats    : optional [n_ligands * 4] uint32 {tree nodes, leaves, table rows used, pair entries}, or NULL
  */

@@ -55,6 +55,8 @@ CASES = {
         dict(n=48, num_conformers=32, seed=6),
         dict(Cation=3.5, Anion=6.0, Aromatic=5.0, HBond_donor=2.0, HBond_acceptor=1.5, Halogen=7.0, Hydrophobic=0.5),
     ),
+    "syn0_c48": ("syn0", dict(n=32, num_conformers=48, seed=12), None),  # two conformers per lane
+    "syn0_c100": ("syn0", dict(n=16, num_conformers=100, seed=13), None),  # four conformers per lane
     "syn0_c4_deep": ("syn0", dict(n=16, num_conformers=4, seed=4, frag_range=(16, 24)), None),  # > 20 clusters
     "loose_c8": ("loose", dict(n=20, num_conformers=8, seed=8), None),
     "xbond_c4": ("xbond", dict(n=32, num_conformers=4, seed=10), None),

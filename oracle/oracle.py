@@ -51,7 +51,7 @@ def max_threads() -> int:
 
 def score(model, batch, weights=None, threads: int = 0, begin: int = 0, end: int | None = None, with_conf=False):
     """model: PackedModel, batch: LigandBatch (host numpy). Returns dict(scores f64[n], status i32[n],
-    stats u64[n,4] = tree nodes, leaves, entries, pair entries[, conf f64[n,64]])."""
+    stats u64[n,4] = tree nodes, leaves, entries, pair entries[, conf f64[n,128]])."""
     L = lib()
     end = batch.num_ligands if end is None else end
     n = end - begin
@@ -65,10 +65,10 @@ def score(model, batch, weights=None, threads: int = 0, begin: int = 0, end: int
     scores = np.zeros(n, dtype=np.float64)
     status = np.zeros(n, dtype=np.int32)
     stats = np.zeros((n, 4), dtype=np.uint64)
-    conf = np.zeros((n, 64), dtype=np.float64) if with_conf else None
+    conf = np.zeros((n, 128), dtype=np.float64) if with_conf else None
     rc = L.pmnet_oracle_score(
         C.byref(ms), C.byref(bs), w.ctypes.data, begin, end, scores.ctypes.data,
-        conf.ctypes.data if with_conf else None, 64, status.ctypes.data, stats.ctypes.data, int(threads),
+        conf.ctypes.data if with_conf else None, 128, status.ctypes.data, stats.ctypes.data, int(threads),
     )  # fmt: skip
     if rc != 0:
         raise RuntimeError(f"pmnet_oracle_score failed with code {rc}")

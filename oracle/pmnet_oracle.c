@@ -32,7 +32,7 @@
 
 #include "../include/pmnet_b200.h"
 
-#define MAXC 64          /* conformers the oracle handles per ligand */
+#define MAXC 128         /* conformers the oracle handles per ligand */
 #define MAXLEV PMNET_MAX_DEPTH
 
 typedef struct {

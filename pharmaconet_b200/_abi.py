@@ -8,7 +8,7 @@ ABI_VERSION = 1
 
 PMNET_OK, PMNET_EINVAL, PMNET_EWORKSPACE, PMNET_ELIMIT, PMNET_ECUDA = range(5)
 LIG_OK, LIG_EMPTY, LIG_OVERFLOW, LIG_UNSUPPORTED = range(4)
-MAX_CONFORMERS = 32
+MAX_CONFORMERS = 128
 
 _u8p = C.POINTER(C.c_uint8)
 _i32p = C.POINTER(C.c_int32)
@@ -57,7 +57,7 @@ class PmScoreConfig(C.Structure):
         ("warps_per_block", C.c_int32),
         ("blocks", C.c_int32),
         ("scratch_rows", C.c_int32),
-        ("reserved", C.c_int32),
+        ("max_conformers", C.c_int32),
     ]
 
 

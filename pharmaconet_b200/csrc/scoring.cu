@@ -59,7 +59,8 @@ struct WarpLayout {
   size_t bytes;     // per warp, multiple of 256
 };
 
-__host__ __device__ inline WarpLayout make_layout(int n_model_clusters, int scratch_rows) {
+// W = 32-conformer words per ligand (1, 2 or 4): every per-conformer row is W * 128 B, every mask W words.
+__host__ __device__ inline WarpLayout make_layout(int n_model_clusters, int scratch_rows, int W) {
   WarpLayout L;
   int t = n_model_clusters * kMaxDepth;
   if (t > 1024) t = 1024;
@@ -70,15 +71,15 @@ __host__ __device__ inline WarpLayout make_layout(int n_model_clusters, int scra
   L.dn_cap = scratch_rows >= 65536 ? 255 : (scratch_rows >= 4096 ? 64 : 32);
   L.rec_cap = L.t_cap * 8;
   size_t o = 0;
-  L.off_rows = o;    o += (size_t)L.rows * 128;
-  L.off_dist = o;    o += (size_t)L.dn_cap * L.dn_cap * 128;
-  L.off_v = o;       o += (size_t)L.pair_cap * 4;
+  L.off_rows = o;    o += (size_t)L.rows * 128 * W;
+  L.off_dist = o;    o += (size_t)L.dn_cap * L.dn_cap * 128 * W;
+  L.off_v = o;       o += (size_t)L.pair_cap * 4 * W;
   L.off_prow = o;    o += (size_t)L.pair_cap * 4;
-  L.off_masks = o;   o += (size_t)kSlots * L.t_cap * 4;
+  L.off_masks = o;   o += (size_t)kSlots * L.t_cap * 4 * W;
   L.off_rowbase = o; o += (size_t)L.t_cap * 4;
   L.off_srow = o;    o += (size_t)L.t_cap * 4;
   L.off_nmoff = o;   o += (size_t)L.t_cap * 4;
-  L.off_geo = o;     o += (size_t)kMaxDepth * 4 * 32 * 4;
+  L.off_geo = o;     o += (size_t)kMaxDepth * 4 * 32 * 4 * W;
   L.off_rec = o;     o += (size_t)L.rec_cap * 8;
   L.off_entmc = o;   o += (size_t)L.t_cap;
   L.off_entlev = o;  o += (size_t)L.t_cap;
@@ -116,8 +117,9 @@ __host__ __device__ inline size_t smem_model_bytes(int nm, int km, int n_cluster
   return align_up(o, 16);
 }
 
+template <int W>
 struct WarpSmem {
-  float tot[kSlots][32];      // per-depth conformer totals
+  float tot[kSlots][W * 32];  // per-depth conformer totals
   int lev_start[kMaxDepth + 1];
   int lev_q[kMaxDepth];       // ligand cluster (global CSR index) of each level
   int lev_nbase[kMaxDepth];   // first local node id of each level
@@ -135,6 +137,7 @@ struct KernelArgs {
   unsigned char* workspace;
   int scratch_rows;
   int n_cluster_nodes;
+  int conf_stride;  // floats per ligand in out_conf (32 * W)
 };
 
 __device__ __forceinline__ float ld_coord(const float* xyz, int stride, int node, int axis, int lane, bool on) {
@@ -165,35 +168,51 @@ __device__ __forceinline__ int rec_model_node(uint2 r, int a, const uint8_t* __r
   return (a < 4) ? (int)((r.y >> (8 * a)) & 255u) : (int)mlist[(r.x >> 16) + a];
 }
 
-// One ligand-node pair against two matched model-node lists (match_utils_numba.py:67-86): returns the fp32
-// likelihood / (M*N) and whether this conformer fails the "half of the pairs within 2 sigma" test.
-__device__ __forceinline__ float pair_term(const SmemModel& sm, const uint8_t* __restrict__ mlist, float d,
-                                           uint2 r1, uint2 r2, bool& fails) {
+// One ligand-node pair against two matched model-node lists (match_utils_numba.py:67-86) for the W conformers of a
+// lane: adds likelihood / (M*N) to sc[] and counts the conformers failing the "half of the pairs within 2 sigma" test.
+template <int W>
+__device__ __forceinline__ void pair_term(const SmemModel& sm, const uint8_t* __restrict__ mlist, const float (&d)[W],
+                                          uint2 r1, uint2 r2, float (&sc)[W], int (&nfail)[W]) {
   const int M = rec_m(r1), N = rec_m(r2);
   if (M == 1 && N == 1) {
     const float4 e = sm.edge[(r1.y & 255u) * sm.nm + (r2.y & 255u)];
-    const float s = __fmul_rn(__fsub_rn(d, e.x), e.y);
-    const float s2 = __fmul_rn(s, s);
-    fails = !(s2 < 4.0f);
-    return e.w * gauss(s2);
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const float s = __fmul_rn(__fsub_rn(d[w], e.x), e.y);
+      const float s2 = __fmul_rn(s, s);
+      nfail[w] += (s2 < 4.0f) ? 0 : 1;
+      sc[w] += e.w * gauss(s2);
+    }
+    return;
   }
-  int npass = 0;
-  float lik = 0.0f;
+  int npass[W];
+  float lik[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    npass[w] = 0;
+    lik[w] = 0.0f;
+  }
   for (int a = 0; a < M; ++a) {
     const float4* row = sm.edge + rec_model_node(r1, a, mlist) * sm.nm;
     for (int b = 0; b < N; ++b) {
       const float4 e = row[rec_model_node(r2, b, mlist)];
-      const float s = __fmul_rn(__fsub_rn(d, e.x), e.y);
-      const float s2 = __fmul_rn(s, s);
-      lik = fmaf(e.w, gauss(s2), lik);
-      npass += (s2 < 4.0f) ? 1 : 0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const float s = __fmul_rn(__fsub_rn(d[w], e.x), e.y);
+        const float s2 = __fmul_rn(s, s);
+        lik[w] = fmaf(e.w, gauss(s2), lik[w]);
+        npass[w] += (s2 < 4.0f) ? 1 : 0;
+      }
     }
   }
   const int mn = M * N;
-  fails = npass < ((mn + 1) >> 1);
   float inv;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"((float)mn));
-  return lik * inv;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    nfail[w] += (npass[w] < ((mn + 1) >> 1)) ? 1 : 0;
+    sc[w] += lik[w] * inv;
+  }
 }
 
 #ifndef PM_BLOCK_THREADS
@@ -202,8 +221,10 @@ __device__ __forceinline__ float pair_term(const SmemModel& sm, const uint8_t* _
 #ifndef PM_MIN_BLOCKS
 #define PM_MIN_BLOCKS 2
 #endif
+template <int W>
 __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_kernel(const KernelArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int CW = 32 * W;  // conformer slots per row
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
@@ -225,8 +246,8 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
     sm.ntype = (uint8_t*)p;          p += align_up((size_t)NM, 4);
     sm.cmask = (uint8_t*)p;          p += align_up((size_t)KM, 4);
   }
-  WarpSmem* ws_all = (WarpSmem*)(smem_raw + smem_model_bytes(NM, KM, args.n_cluster_nodes));
-  WarpSmem& ws = ws_all[warp_in_block];
+  WarpSmem<W>* ws_all = (WarpSmem<W>*)(smem_raw + smem_model_bytes(NM, KM, args.n_cluster_nodes));
+  WarpSmem<W>& ws = ws_all[warp_in_block];
 
   for (int i = threadIdx.x; i < NM * NM; i += blockDim.x) {
     const int a = i / NM, b = i % NM;
@@ -248,7 +269,7 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
   __syncthreads();
 
   // ---- per-warp scratch
-  const WarpLayout LY = make_layout(KM, args.scratch_rows);
+  const WarpLayout LY = make_layout(KM, args.scratch_rows, W);
   const int gwarp = blockIdx.x * warps_per_block + warp_in_block;
   unsigned char* wbase = args.workspace + kHeaderBytes + (size_t)gwarp * LY.bytes;
   float* const rows = (float*)(wbase + LY.off_rows);
@@ -280,9 +301,11 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
     float score_out = 0.0f;
     int status = PMNET_LIG_OK;
     uint32_t st_nodes = 0, st_leaves = 0, st_rows = 0, st_pairs = 0;
-    float best = 0.0f;
+    float best[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) best[w] = 0.0f;
 
-    if (C < 1 || C > PMNET_MAX_CONFORMERS) {
+    if (C < 1 || C > CW) {
       status = PMNET_LIG_UNSUPPORTED;
     } else {
       const int stride = (C + 3) & ~3;
@@ -290,8 +313,16 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
       const uint8_t* tmask = B.node_type_mask + (B.lig_node_off[lig] - B.node_base);
       const int q0 = B.lig_cluster_off[lig] - B.cluster_base, q1 = B.lig_cluster_off[lig + 1] - B.cluster_base;
       const uint8_t* cl_nodes = B.cluster_nodes - B.cnode_base;  // indexed with the stored (un-rebased) offsets
-      const bool on = lane < C;
-      const unsigned cmask_full = (C == 32) ? kFull : ((1u << C) - 1u);
+      bool on[W];
+      unsigned cfull[W];  // conformer mask words of this ligand
+      bool lane_on = false;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        on[w] = lane + 32 * w < C;
+        lane_on |= on[w];
+        const int rem = C - 32 * w;
+        cfull[w] = rem >= 32 ? kFull : (rem > 0 ? ((1u << rem) - 1u) : 0u);
+      }
 
       // ================= phase 0: levels, entries, node-match records (graph_match.py:85-92, 124-172)
       int L = 0, T = 0, NL = 0;
@@ -332,29 +363,33 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
           // the level's nodes get consecutive local ids (cluster order, ligand.py:387-395)
           for (int i = lane; i < n; i += 32) lnode[NL + i] = cl_nodes[c0 + i];
           // cluster centre and size per conformer (ligand.py:458-473), fp32 sequential like numpy
-          float cx = 0.f, cy = 0.f, cz = 0.f;
-          for (int i = c0; i < c1; ++i) {
-            const int node = cl_nodes[i];
-            const float x = ld_coord(xyz, stride, node, 0, lane, on), y = ld_coord(xyz, stride, node, 1, lane, on),
-                        z = ld_coord(xyz, stride, node, 2, lane, on);
-            if (i == c0) {
-              cx = x; cy = y; cz = z;
-            } else {
-              cx = __fadd_rn(cx, x); cy = __fadd_rn(cy, y); cz = __fadd_rn(cz, z);
-            }
-          }
           const float fn = (float)n;
-          cx = __fdiv_rn(cx, fn); cy = __fdiv_rn(cy, fn); cz = __fdiv_rn(cz, fn);
-          float sz = 0.f;
-          for (int i = c0; i < c1; ++i) {
-            const int node = cl_nodes[i];
-            const float d = norm3(__fsub_rn(ld_coord(xyz, stride, node, 0, lane, on), cx),
-                                  __fsub_rn(ld_coord(xyz, stride, node, 1, lane, on), cy),
-                                  __fsub_rn(ld_coord(xyz, stride, node, 2, lane, on), cz));
-            sz = (i == c0) ? d : fmaxf(sz, d);
+#pragma unroll
+          for (int w = 0; w < W; ++w) {
+            const int c = lane + 32 * w;
+            float cx = 0.f, cy = 0.f, cz = 0.f;
+            for (int i = c0; i < c1; ++i) {
+              const int node = cl_nodes[i];
+              const float x = ld_coord(xyz, stride, node, 0, c, on[w]), y = ld_coord(xyz, stride, node, 1, c, on[w]),
+                          z = ld_coord(xyz, stride, node, 2, c, on[w]);
+              if (i == c0) {
+                cx = x; cy = y; cz = z;
+              } else {
+                cx = __fadd_rn(cx, x); cy = __fadd_rn(cy, y); cz = __fadd_rn(cz, z);
+              }
+            }
+            cx = __fdiv_rn(cx, fn); cy = __fdiv_rn(cy, fn); cz = __fdiv_rn(cz, fn);
+            float sz = 0.f;
+            for (int i = c0; i < c1; ++i) {
+              const int node = cl_nodes[i];
+              const float d = norm3(__fsub_rn(ld_coord(xyz, stride, node, 0, c, on[w]), cx),
+                                    __fsub_rn(ld_coord(xyz, stride, node, 1, c, on[w]), cy),
+                                    __fsub_rn(ld_coord(xyz, stride, node, 2, c, on[w]), cz));
+              sz = (i == c0) ? d : fmaxf(sz, d);
+            }
+            float* g = geo + (size_t)L * 4 * CW + c;
+            g[0] = cx; g[CW] = cy; g[2 * CW] = cz; g[3 * CW] = sz;
           }
-          float* g = geo + (size_t)L * 128;
-          g[lane] = cx; g[32 + lane] = cy; g[64 + lane] = cz; g[96 + lane] = sz;
           NL += n;
           ++L;
         }
@@ -445,14 +480,24 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
         if (!overflow) {
           for (int i = 0; i < NL - 1; ++i) {
             const int ni = lnode[i];
-            const float xi = ld_coord(xyz, stride, ni, 0, lane, on), yi = ld_coord(xyz, stride, ni, 1, lane, on),
-                        zi = ld_coord(xyz, stride, ni, 2, lane, on);
-            float* drow = dist + ((size_t)i * NL) * 32 + lane;
+            float xi[W], yi[W], zi[W];
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+              const int c = lane + 32 * w;
+              xi[w] = ld_coord(xyz, stride, ni, 0, c, on[w]);
+              yi[w] = ld_coord(xyz, stride, ni, 1, c, on[w]);
+              zi[w] = ld_coord(xyz, stride, ni, 2, c, on[w]);
+            }
+            float* drow = dist + ((size_t)i * NL) * CW + lane;
             for (int j = i + 1; j < NL; ++j) {
               const int nj = lnode[j];
-              drow[(size_t)j * 32] = norm3(__fsub_rn(xi, ld_coord(xyz, stride, nj, 0, lane, on)),
-                                          __fsub_rn(yi, ld_coord(xyz, stride, nj, 1, lane, on)),
-                                          __fsub_rn(zi, ld_coord(xyz, stride, nj, 2, lane, on)));
+#pragma unroll
+              for (int w = 0; w < W; ++w) {
+                const int c = lane + 32 * w;
+                drow[(size_t)j * CW + 32 * w] = norm3(__fsub_rn(xi[w], ld_coord(xyz, stride, nj, 0, c, on[w])),
+                                                      __fsub_rn(yi[w], ld_coord(xyz, stride, nj, 1, c, on[w])),
+                                                      __fsub_rn(zi[w], ld_coord(xyz, stride, nj, 2, c, on[w])));
+              }
             }
           }
         }
@@ -470,15 +515,23 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
           const int cnt = nmcnt[e];
           int r = -1;
           if (cnt >= 2) {
-            float sc = 0.0f;
+            float sc[W];
+            int nf[W];
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+              sc[w] = 0.0f;
+              nf[w] = 0;
+            }
             const uint32_t off = nmoff[e];
             for (int i = 0; i < cnt - 1; ++i) {
               const uint2 r1 = rec[off + i];
-              const float* drow = dist + ((size_t)rec_node(r1) * NL) * 32 + lane;
+              const float* drow = dist + ((size_t)rec_node(r1) * NL) * CW + lane;
               for (int j = i + 1; j < cnt; ++j) {
                 const uint2 r2 = rec[off + j];
-                bool f;
-                sc += pair_term(sm, mlist, drow[(size_t)rec_node(r2) * 32], r1, r2, f);
+                float d[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) d[w] = drow[(size_t)rec_node(r2) * CW + 32 * w];
+                pair_term<W>(sm, mlist, d, r1, r2, sc, nf);
               }
             }
             if (nrows >= LY.rows) {
@@ -486,18 +539,28 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
               break;
             }
             r = nrows++;
-            rows[(size_t)r * 32 + lane] = sc;
+#pragma unroll
+            for (int w = 0; w < W; ++w) rows[((size_t)r * W + w) * 32 + lane] = sc[w];
           }
           if (lane == 0) srow[e] = r;
         }
         for (int i = 0; i < L - 1 && !overflow; ++i) {
-          const float* gi = geo + (size_t)i * 128;
-          const float cix = gi[lane], ciy = gi[32 + lane], ciz = gi[64 + lane], csi = gi[96 + lane];
+          const float* gi = geo + (size_t)i * 4 * CW + lane;
+          float cix[W], ciy[W], ciz[W], csi[W];
+#pragma unroll
+          for (int w = 0; w < W; ++w) {
+            cix[w] = gi[32 * w]; ciy[w] = gi[CW + 32 * w]; ciz[w] = gi[2 * CW + 32 * w]; csi[w] = gi[3 * CW + 32 * w];
+          }
           const int s1 = ws.lev_start[i], e1_end = ws.lev_start[i + 1];
           for (int j = i + 1; j < L && !overflow; ++j) {
-            const float* gj = geo + (size_t)j * 128;
-            const float ldist = norm3(__fsub_rn(cix, gj[lane]), __fsub_rn(ciy, gj[32 + lane]), __fsub_rn(ciz, gj[64 + lane]));
-            const float lsize = __fadd_rn(csi, gj[96 + lane]);
+            const float* gj = geo + (size_t)j * 4 * CW + lane;
+            float ldist[W], lsize[W];
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+              ldist[w] = norm3(__fsub_rn(cix[w], gj[32 * w]), __fsub_rn(ciy[w], gj[CW + 32 * w]),
+                               __fsub_rn(ciz[w], gj[2 * CW + 32 * w]));
+              lsize[w] = __fadd_rn(csi[w], gj[3 * CW + 32 * w]);
+            }
             const int s2 = ws.lev_start[j], e2_end = ws.lev_start[j + 1];
             for (int e1 = s1; e1 < e1_end && !overflow; ++e1) {
               const int k = entmc[e1];
@@ -509,45 +572,68 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
               for (int e2 = s2; e2 < e2_end; ++e2) {
                 const int l = entmc[e2];
                 // cluster prefilter (graph_match.py:263-268): min_c(|d_lig - d_mod| - size_lig) > size_mod
-                const float v = __fsub_rn(fabsf(__fsub_rn(ldist, cd[l])), lsize);
-                const bool far = !on || (v > cs[l]);
-                unsigned valid = 0;
+                const float cdl = cd[l], csl = cs[l];
+                bool far = true;
+#pragma unroll
+                for (int w = 0; w < W; ++w)
+                  far &= !on[w] || (__fsub_rn(fabsf(__fsub_rn(ldist[w], cdl)), lsize[w]) > csl);
+                unsigned valid[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) valid[w] = 0;
+                bool anyvalid = false;
                 int r = -1;
                 if (!__all_sync(kFull, far)) {
                   const int cnt2 = nmcnt[e2];
                   const uint32_t off2 = nmoff[e2];
                   const int thr2 = cnt1 * cnt2;  // fail <= 0.5*cnt1*cnt2  <=>  2*fail <= cnt1*cnt2
-                  float sc = 0.0f;
-                  int nfail = 0;
+                  float sc[W];
+                  int nfail[W];
+#pragma unroll
+                  for (int w = 0; w < W; ++w) {
+                    sc[w] = 0.0f;
+                    nfail[w] = 0;
+                  }
                   bool dead = false;
                   for (int a = 0; a < cnt1; ++a) {
                     const uint2 r1 = rec[off1 + a];
-                    const float* drow = dist + ((size_t)rec_node(r1) * NL) * 32 + lane;
+                    const float* drow = dist + ((size_t)rec_node(r1) * NL) * CW + lane;
                     for (int b = 0; b < cnt2; ++b) {
                       const uint2 r2 = rec[off2 + b];
-                      bool f;
-                      sc += pair_term(sm, mlist, drow[(size_t)rec_node(r2) * 32], r1, r2, f);
-                      nfail += f ? 1 : 0;
+                      float d[W];
+#pragma unroll
+                      for (int w = 0; w < W; ++w) d[w] = drow[(size_t)rec_node(r2) * CW + 32 * w];
+                      pair_term<W>(sm, mlist, d, r1, r2, sc, nfail);
                     }
                     // every conformer already failed: the pair is invalid whatever follows
                     // (match_utils_numba.py:191-192 tests this after every term; the outcome is the same)
-                    if (__all_sync(kFull, !on || (2 * nfail > thr2))) {
+                    bool alldead = true;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) alldead &= !on[w] || (2 * nfail[w] > thr2);
+                    if (__all_sync(kFull, alldead)) {
                       dead = true;
                       break;
                     }
                   }
-                  if (!dead) valid = __ballot_sync(kFull, on && (2 * nfail <= thr2) && (sc > 0.0f));
-                  if (valid) {
+                  if (!dead) {
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                      valid[w] = __ballot_sync(kFull, on[w] && (2 * nfail[w] <= thr2) && (sc[w] > 0.0f));
+                      anyvalid |= valid[w] != 0;
+                    }
+                  }
+                  if (anyvalid) {
                     if (nrows >= LY.rows) {
                       overflow = true;
                       break;
                     }
                     r = nrows++;
-                    rows[(size_t)r * 32 + lane] = sc;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) rows[((size_t)r * W + w) * 32 + lane] = sc[w];
                   }
                 }
                 if (lane == 0) {
-                  Vt[pb + e2] = valid;
+#pragma unroll
+                  for (int w = 0; w < W; ++w) Vt[(size_t)(pb + e2) * W + w] = valid[w];
                   prow[pb + e2] = r;
                 }
               }
@@ -563,12 +649,17 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
           // ================= phase 2: DFS (tree.py:55-104) with an explicit stack; lane d holds depth d's state
           int st_cursor = 0, st_maxm = 0, st_nchild = 0, st_phase = 0, st_nmatch = 0, st_entry = -1, st_mslot = 0,
               st_tslot = 0, st_pbase = 0;
-          unsigned st_alive = 0;
-          for (int e = lane; e < T; e += 32) masks[e] = cmask_full;
-          ws.tot[0][lane] = 0.0f;
+          unsigned st_alive[W];
+#pragma unroll
+          for (int w = 0; w < W; ++w) {
+            st_alive[w] = 0;
+            for (int e = lane; e < T; e += 32) masks[(size_t)e * W + w] = cfull[w];
+            ws.tot[0][32 * w + lane] = 0.0f;
+          }
           if (lane == 0) {
             st_cursor = 0;  // lev_start[0]
-            st_alive = cmask_full;
+#pragma unroll
+            for (int w = 0; w < W; ++w) st_alive[w] = cfull[w];
           }
           __syncwarp();
           st_nodes = 1;
@@ -579,21 +670,30 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
             const int phase = __shfl_sync(kFull, st_phase, d);
             const int mslot = __shfl_sync(kFull, st_mslot, d);
             const int tslot = __shfl_sync(kFull, st_tslot, d);
-            const uint32_t* pm = masks + (size_t)mslot * LY.t_cap;
+            const uint32_t* pm = masks + (size_t)mslot * LY.t_cap * W;
             bool do_return = false;
             if (phase == 0) {
               int cur = __shfl_sync(kFull, st_cursor, d);
               const int end = ws.lev_start[y + 1];
               int found = -1;
-              unsigned alive2 = 0;
+              unsigned alive2[W];
+#pragma unroll
+              for (int w = 0; w < W; ++w) alive2[w] = 0;
               while (cur < end) {
                 const int idx = cur + lane;
-                const unsigned mw = (idx < end) ? pm[idx] : 0u;
-                const unsigned bal = __ballot_sync(kFull, mw != 0u);
+                unsigned mw[W];
+                unsigned anyw = 0;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                  mw[w] = (idx < end) ? pm[(size_t)idx * W + w] : 0u;
+                  anyw |= mw[w];
+                }
+                const unsigned bal = __ballot_sync(kFull, anyw != 0u);
                 if (bal) {
                   const int src = __ffs(bal) - 1;
                   found = cur + src;
-                  alive2 = __shfl_sync(kFull, mw, src);
+#pragma unroll
+                  for (int w = 0; w < W; ++w) alive2[w] = __shfl_sync(kFull, mw[w], src);
                   break;
                 }
                 cur += 32;
@@ -609,7 +709,9 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
                 // are added in top-down order like the reference's running sums (tree.py:78-82)
                 const int myrow = (lane >= 1 && lane <= d && st_entry >= 0) ? prow[st_pbase + found] : -1;
                 unsigned anc = __ballot_sync(kFull, myrow >= 0);
-                float acc = 0.0f;
+                float acc[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) acc[w] = 0.0f;
                 while (anc) {
                   // four independent row loads in flight per round; the adds stay in top-down order
                   int rr[4];
@@ -620,28 +722,45 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
                     rr[u] = anc ? r : -1;
                     anc &= anc - 1;
                   }
-                  float vv[4];
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) vv[u] = (rr[u] >= 0) ? rows[(size_t)rr[u] * 32 + lane] : 0.0f;
+                  float vv[4][W];
 #pragma unroll
                   for (int u = 0; u < 4; ++u)
-                    if (rr[u] >= 0) acc += vv[u];
+#pragma unroll
+                    for (int w = 0; w < W; ++w)
+                      vv[u][w] = (rr[u] >= 0) ? rows[((size_t)rr[u] * W + w) * 32 + lane] : 0.0f;
+#pragma unroll
+                  for (int u = 0; u < 4; ++u)
+                    if (rr[u] >= 0) {
+#pragma unroll
+                      for (int w = 0; w < W; ++w) acc[w] += vv[u][w];
+                    }
                 }
-                float t = ws.tot[tslot][lane];
+                float t[W];
                 const int sr = srow[found];
-                if (sr >= 0) t += rows[(size_t)sr * 32 + lane];
-                t += acc;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                  t[w] = ws.tot[tslot][32 * w + lane];
+                  if (sr >= 0) t[w] += rows[((size_t)sr * W + w) * 32 + lane];
+                  t[w] += acc[w];
+                }
                 if (y == L - 1) {
                   // leaf (graph_match.py:103-109)
                   ++st_leaves;
-                  if ((alive2 >> lane) & 1u) best = fmaxf(best, t);
+#pragma unroll
+                  for (int w = 0; w < W; ++w)
+                    if ((alive2[w] >> lane) & 1u) best[w] = fmaxf(best[w], t[w]);
                   if (lane == d) st_maxm = max(st_maxm, 1);
                 } else {
                   const int nmatch = __shfl_sync(kFull, st_nmatch, d) + 1;
                   const int pbc = rowbase[found];
-                  uint32_t* nm_ = masks + (size_t)(d + 1) * LY.t_cap;
-                  for (int e2 = ws.lev_start[y + 1] + lane; e2 < T; e2 += 32) nm_[e2] = pm[e2] & alive2 & Vt[pbc + e2];
-                  ws.tot[d + 1][lane] = t;
+                  uint32_t* nm_ = masks + (size_t)(d + 1) * LY.t_cap * W;
+                  for (int e2 = ws.lev_start[y + 1] + lane; e2 < T; e2 += 32) {
+#pragma unroll
+                    for (int w = 0; w < W; ++w)
+                      nm_[(size_t)e2 * W + w] = pm[(size_t)e2 * W + w] & alive2[w] & Vt[(size_t)(pbc + e2) * W + w];
+                  }
+#pragma unroll
+                  for (int w = 0; w < W; ++w) ws.tot[d + 1][32 * w + lane] = t[w];
                   if (lane == d + 1) {
                     st_cursor = ws.lev_start[y + 1];
                     st_maxm = 0;
@@ -652,7 +771,8 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
                     st_mslot = d + 1;
                     st_tslot = d + 1;
                     st_pbase = pbc;
-                    st_alive = alive2;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) st_alive[w] = alive2[w];
                   }
                   __syncwarp();
                   d = d + 1;
@@ -666,11 +786,16 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
               if (nchild == 0 || nmatch + maxm < PMNET_MIN_MATCHES) {
                 ++st_nodes;
                 if (lane == d) st_phase = 1;
-                const unsigned alive = __shfl_sync(kFull, st_alive, d);
+                unsigned alive[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) alive[w] = __shfl_sync(kFull, st_alive[w], d);
                 if (y == L - 1) {
                   ++st_leaves;
-                  const float t = ws.tot[tslot][lane];
-                  if ((alive >> lane) & 1u) best = fmaxf(best, t);
+#pragma unroll
+                  for (int w = 0; w < W; ++w) {
+                    const float t = ws.tot[tslot][32 * w + lane];
+                    if ((alive[w] >> lane) & 1u) best[w] = fmaxf(best[w], t);
+                  }
                   do_return = true;
                 } else {
                   if (lane == d + 1) {
@@ -683,7 +808,8 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
                     st_mslot = mslot;
                     st_tslot = tslot;
                     st_pbase = 0;
-                    st_alive = alive;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) st_alive[w] = alive[w];
                   }
                   d = d + 1;
                   continue;
@@ -702,11 +828,14 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
             }
           }
           // mean over conformers (graph_match.py:109)
-          double s = on ? (double)best : 0.0;
+          double s = 0.0;
+#pragma unroll
+          for (int w = 0; w < W; ++w) s += on[w] ? (double)best[w] : 0.0;
           for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
           score_out = (float)(s / (double)C);
         }
       }
+      (void)lane_on;
     }
     if (lane == 0) {
       args.out_scores[lig] = score_out;
@@ -719,10 +848,16 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
         o[3] = st_pairs;
       }
     }
-    if (args.out_conf) args.out_conf[(size_t)lig * 32 + lane] = (status == PMNET_LIG_OK) ? best : 0.0f;
+    if (args.out_conf) {
+#pragma unroll
+      for (int w = 0; w < W; ++w)
+        if (32 * w < args.conf_stride)
+          args.out_conf[(size_t)lig * args.conf_stride + 32 * w + lane] = (status == PMNET_LIG_OK) ? best[w] : 0.0f;
+    }
     __syncwarp();
   }
 }
+
 
 int sm_count_cached() {
   static int n = 0;
@@ -742,8 +877,12 @@ void resolve_cfg(const PmScoreConfig* in, PmScoreConfig* out, bool query_device)
   if (c.warps_per_block > kMaxWarps) c.warps_per_block = kMaxWarps;
   if (c.blocks <= 0) c.blocks = PM_MIN_BLOCKS * (query_device ? sm_count_cached() : 148);
   if (c.scratch_rows <= 0) c.scratch_rows = 8192;
+  if (c.max_conformers <= 0) c.max_conformers = 32;
   *out = c;
 }
+
+// 32-conformer words per ligand for a launch that must handle up to `max_conformers` conformers
+int conf_words(int max_conformers) { return max_conformers <= 32 ? 1 : (max_conformers <= 64 ? 2 : 4); }
 
 }  // namespace
 
@@ -760,7 +899,7 @@ size_t pmnet_score_workspace_bytes(int32_t n_model_nodes, int32_t n_model_cluste
   (void)n_model_nodes;
   PmScoreConfig c;
   resolve_cfg(cfg, &c, cfg == nullptr || cfg->blocks <= 0);
-  const WarpLayout L = make_layout(n_model_clusters, c.scratch_rows);
+  const WarpLayout L = make_layout(n_model_clusters, c.scratch_rows, conf_words(c.max_conformers));
   return kHeaderBytes + (size_t)c.blocks * c.warps_per_block * L.bytes;
 }
 
@@ -809,19 +948,32 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
   }
   cudaError_t e;
   a.n_cluster_nodes = n_cluster_nodes;
-  const size_t smem = smem_model_bytes(model->n_nodes, model->n_clusters, n_cluster_nodes) +
-                      (size_t)c.warps_per_block * sizeof(WarpSmem);
+  if (c.max_conformers > PMNET_MAX_CONFORMERS) {
+    set_err("pmnet_score_batch: max_conformers exceeds PMNET_MAX_CONFORMERS");
+    return PMNET_ELIMIT;
+  }
+  const int W = conf_words(c.max_conformers);
+  a.conf_stride = 32 * W;
+  const size_t wsm = W == 1 ? sizeof(WarpSmem<1>) : (W == 2 ? sizeof(WarpSmem<2>) : sizeof(WarpSmem<4>));
+  const size_t smem = smem_model_bytes(model->n_nodes, model->n_clusters, n_cluster_nodes) + (size_t)c.warps_per_block * wsm;
   if (smem > 200 * 1024) {
     set_err("pmnet_score_batch: model tables do not fit in shared memory");
     return PMNET_ELIMIT;
   }
-  e = cudaFuncSetAttribute(pmnet_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const void* fn = W == 1 ? (const void*)pmnet_score_kernel<1>
+                          : (W == 2 ? (const void*)pmnet_score_kernel<2> : (const void*)pmnet_score_kernel<4>);
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) e = cudaMemsetAsync(workspace, 0, kHeaderBytes, stream);
   if (e != cudaSuccess) {
     set_err(cudaGetErrorString(e));
     return PMNET_ECUDA;
   }
-  pmnet_score_kernel<<<c.blocks, c.warps_per_block * 32, smem, stream>>>(a);
+  if (W == 1)
+    pmnet_score_kernel<1><<<c.blocks, c.warps_per_block * 32, smem, stream>>>(a);
+  else if (W == 2)
+    pmnet_score_kernel<2><<<c.blocks, c.warps_per_block * 32, smem, stream>>>(a);
+  else
+    pmnet_score_kernel<4><<<c.blocks, c.warps_per_block * 32, smem, stream>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_err(cudaGetErrorString(e));

@@ -56,11 +56,16 @@ class DeviceLigandBatch:
         n_ligands: int,
         n_conformers_total: int,
         bases: dict[str, int] | None = None,
+        max_conformers: int | None = None,
     ):
-        """bases: for a block of a larger library whose CSR offsets were not re-based (see include/pmnet_b200.h)."""
+        """bases: for a block of a larger library whose CSR offsets were not re-based (see include/pmnet_b200.h).
+        max_conformers: largest n_conf in the batch (read back from the device when not given)."""
         self.tensors = tensors
         self.n_ligands = int(n_ligands)
         self.n_conformers_total = int(n_conformers_total)
+        if max_conformers is None:
+            max_conformers = int(tensors["n_conf"][: self.n_ligands].max().item()) if self.n_ligands else 1
+        self.max_conformers = int(max_conformers)
         self.device = tensors["coords"].device
         self.struct = _abi.batch_struct(
             self.n_ligands, {k: tensors[k].data_ptr() for k in _abi.BATCH_FIELDS}, bases
@@ -73,7 +78,7 @@ class DeviceLigandBatch:
             k: torch.from_numpy(np.ascontiguousarray(v)).to(device, non_blocking=non_blocking)
             for k, v in batch.arrays().items()
         }
-        return cls(t, batch.num_ligands, batch.num_conformers_total)
+        return cls(t, batch.num_ligands, batch.num_conformers_total, max_conformers=max(1, batch.max_conformers))
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self.tensors.values())
@@ -85,8 +90,13 @@ class ScoreConfig:
     blocks: int = 0
     scratch_rows: int = 0
 
-    def struct(self) -> _abi.PmScoreConfig:
-        return _abi.PmScoreConfig(self.warps_per_block, self.blocks, self.scratch_rows, 0)
+    def struct(self, max_conformers: int = 32) -> _abi.PmScoreConfig:
+        return _abi.PmScoreConfig(self.warps_per_block, self.blocks, self.scratch_rows, int(max_conformers))
+
+
+def conf_stride(max_conformers: int) -> int:
+    """Row length of the per-conformer output: 32 conformers per lane word, 1 / 2 / 4 words."""
+    return 32 if max_conformers <= 32 else (64 if max_conformers <= 64 else 128)
 
 
 def big_config(model) -> ScoreConfig:
@@ -94,7 +104,7 @@ def big_config(model) -> ScoreConfig:
     worst case of this model (T = min(20 Km, 1024) entries, T^2/2 pairs), on fewer warps."""
     t = min(20 * model.num_clusters, 1024)
     rows = max(65536, t * t // 2 + t)  # >= 65536 rows also selects the 255-node distance table
-    return ScoreConfig(warps_per_block=4, blocks=32, scratch_rows=rows)
+    return ScoreConfig(warps_per_block=4, blocks=16, scratch_rows=rows)
 
 
 _workspaces: dict[tuple, torch.Tensor] = {}
@@ -113,8 +123,8 @@ def release_workspaces() -> None:
     _workspaces.clear()
 
 
-def workspace_bytes(model: "DeviceModel", config: "ScoreConfig | None" = None) -> int:
-    cfg = (config or ScoreConfig()).struct()
+def workspace_bytes(model: "DeviceModel", config: "ScoreConfig | None" = None, max_conformers: int = 32) -> int:
+    cfg = (config or ScoreConfig()).struct(max_conformers)
     with torch.cuda.device(model.device):
         return int(_lib.lib().pmnet_score_workspace_bytes(model.num_nodes, model.num_clusters, C.byref(cfg)))
 
@@ -136,7 +146,9 @@ def score_batch(
     L = _lib.lib()
     dev = model.device
     n = batch.n_ligands
-    cfg = (config or ScoreConfig()).struct()
+    if batch.max_conformers > _abi.MAX_CONFORMERS:
+        raise ValueError(f"ligands with more than {_abi.MAX_CONFORMERS} conformers are not supported")
+    cfg = (config or ScoreConfig()).struct(batch.max_conformers)
     with torch.cuda.device(dev):
         need = L.pmnet_score_workspace_bytes(model.num_nodes, model.num_clusters, C.byref(cfg))
         if workspace is None:
@@ -148,7 +160,7 @@ def score_batch(
         scores = out_scores if out_scores is not None else torch.empty(n, dtype=torch.float32, device=dev)
         status = out_status if out_status is not None else torch.empty(n, dtype=torch.int32, device=dev)
         stats = torch.zeros((n, 4), dtype=torch.int32, device=dev) if with_stats else None
-        conf = torch.zeros((n, 32), dtype=torch.float32, device=dev) if with_conf else None
+        conf = torch.zeros((n, conf_stride(batch.max_conformers)), dtype=torch.float32, device=dev) if with_conf else None
         w = (C.c_float * 7)(*weights_vector(weights))
         s = stream if stream is not None else torch.cuda.current_stream(dev)
         rc = L.pmnet_score_batch(

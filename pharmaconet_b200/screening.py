@@ -194,7 +194,7 @@ class Screener:
         main = torch.cuda.current_stream(dev)
         start = torch.cuda.Event()
         start.record(main)
-        need = workspace_bytes(self.model, self.config)
+        need = workspace_bytes(self.model, self.config, max(1, lib.max_conformers))
         pos = 0
         spans = []
         for it, (a, b) in enumerate(blocks):
@@ -216,7 +216,7 @@ class Screener:
             nb = b - a
             nc = int(lib.n_conf[a:b].sum())
             n_conf += nc
-            db = DeviceLigandBatch(views, nb, nc, bases)
+            db = DeviceLigandBatch(views, nb, nc, bases, max_conformers=int(lib.n_conf[a:b].max()))
             if it < 2:
                 slot.stream.wait_event(start)
             slot.stream.wait_event(slot.ready)

@@ -373,4 +373,4 @@ def make_library_device(
     )
     tensors = {k: torch.from_numpy(v).to(dev) for k, v in host.items()}
     tensors["coords"] = coords
-    return DeviceLigandBatch(tensors, n_ligands, n_ligands * C)
+    return DeviceLigandBatch(tensors, n_ligands, n_ligands * C, max_conformers=C)

@@ -185,3 +185,22 @@ def test_screening_cli_on_packed_library(tmp_path):
     assert vals == sorted(vals, reverse=True)  # screening.py:70 sorts by score, descending
     ref = dict(zip(names, c["ref"]))
     assert max(abs(got[n] - ref[n]) / max(abs(ref[n]), 1e-12) for n in names) <= REL_TOL
+
+
+def test_more_than_32_conformers_mixed_batch():
+    # 2 and 4 conformers per lane, mixed with short ligands in the same launch; per-conformer maxima too
+    c = load_case("syn0_c100")
+    ligs = synthetic.make_ligands(40, 70, seed=31) + synthetic.make_ligands(40, 7, seed=32) + synthetic.make_ligands(8, 128, seed=33)
+    batch = LigandBatch.from_typed(ligs)
+    out = _run(c["model"], batch, None)
+    o = orc.score(c["model"], batch, None, with_conf=True)
+    assert np.array_equal(out["status"], o["status"]) and np.all(out["status"] == _abi.LIG_OK)
+    assert rel_err(out["scores"], o["scores"]).max() <= REL_TOL
+    assert np.array_equal(out["stats"][:, 0].astype(np.uint64), o["stats"][:, 0])
+    dm = scoring.DeviceModel(c["model"], "cuda:0")
+    conf = scoring.score_batch(dm, scoring.DeviceLigandBatch.from_host(batch, "cuda:0"), with_conf=True)["conf"]
+    assert conf.shape == (88, 128)
+    assert np.abs(conf.cpu().numpy() - o["conf"]).max() <= REL_TOL * np.abs(o["conf"]).max()
+    too_many = LigandBatch.from_typed(synthetic.make_ligands(2, 130, seed=34))
+    with pytest.raises(ValueError):
+        scoring.score_batch(dm, scoring.DeviceLigandBatch.from_host(too_many, "cuda:0"))
