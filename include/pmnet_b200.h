@@ -183,6 +183,21 @@ int pmnet_density_post(const float* logits, const int32_t* tokens, const uint8_t
                        const uint8_t* cavity_mask, const float* taps3, float threshold, float* out, int32_t n,
                        int32_t size, void* stream);
 
+/* Window attention of a 3-D Swin-V2 block (swinv2.py:114-158, 272-298): cyclic shift (first two spatial axes only,
+ * like the reference), 4^3 window partition, cosine attention with per-head logit scale, continuous position bias,
+ * shift mask, softmax, P.V, window reverse and un-shift in one kernel.
+ *   qkv  : [B * res^3][3 * heads * 32] token-major (q | k | v), fp32 or bf16; out : [B * res^3][heads * 32], same type
+ *   logit_scale : fp32 [heads] = exp(min(logit_scale, log 100)); rel_bias : fp32 [heads][64][64] =
+ *   16 * sigmoid(cpb_mlp(table))[index]; attn_mask : fp32 [(res/4)^3][64][64] or NULL (shift = 0) */
+int pmnet_window_attention(const void* qkv, void* out, const float* logit_scale, const float* rel_bias,
+                           const float* attn_mask, int32_t B, int32_t res, int32_t shift, int32_t heads,
+                           int32_t is_bf16, void* stream);
+
+/* y = shortcut + LayerNorm(h) * gamma + beta (res-post-norm, swinv2.py:300-303); shortcut may be NULL (plain
+ * LayerNorm) and may alias y. h fp32 or bf16 [rows][C]; y, shortcut fp32; C in {96, 192, 384, 768}. */
+int pmnet_ln_residual(const float* shortcut, const void* h, int32_t h_is_bf16, const float* gamma, const float* beta,
+                      float* y, int64_t rows, int32_t C, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

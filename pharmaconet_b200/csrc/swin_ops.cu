@@ -1,0 +1,218 @@
+// swin_ops.cu - the non-GEMM part of a 3-D Swin-V2 block in two kernels (the GEMMs stay plain library GEMMs).
+//
+//  pmnet_window_attention  cyclic shift + window partition + cosine attention + continuous position bias + shift
+//                          mask + softmax + P.V + window reverse + un-shift, one read of qkv and one write of the
+//                          result per token (src/pmnet/network/backbones/swinv2.py:114-158, 272-298,
+//                          swin.py:46-96). Reference quirk kept: the shift rolls only the first two spatial axes
+//                          (swinv2.py:277,296).
+//  pmnet_ln_residual       x = shortcut + LayerNorm(h) (res-post-norm, swinv2.py:300-303), one warp per token.
+//
+// Both are memory-bound: the reference's eager sequence makes ~25 passes over the token tensor per block, these
+// make 4 (qkv read, attention write, two LayerNorm passes). fp32 arithmetic; storage fp32 or bf16.
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pmnet_b200.h"
+
+extern void pmnet_set_error(const char* msg);
+
+namespace {
+
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p);
+template <>
+__device__ __forceinline__ float ldf<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T>
+__device__ __forceinline__ void stf(T* p, float v);
+template <>
+__device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+constexpr int kHeadDim = 32;
+constexpr int kTokens = 64;  // 4^3 window
+
+// grid (windows, heads), block 64: thread t = token t of the window.
+template <typename T>
+__global__ void __launch_bounds__(kTokens) window_attention_kernel(const T* __restrict__ qkv, T* __restrict__ out,
+                                                                   const float* __restrict__ scale,
+                                                                   const float* __restrict__ rel_bias,
+                                                                   const float* __restrict__ mask, int res, int shift,
+                                                                   int heads) {
+  __shared__ float ks[kTokens][kHeadDim + 1];
+  __shared__ float vs[kTokens][kHeadDim];
+  const int t = threadIdx.x, h = blockIdx.y;
+  const int nw1 = res / 4, nw = nw1 * nw1 * nw1;
+  const int win = blockIdx.x % nw, b = blockIdx.x / nw;
+  const int wd = win / (nw1 * nw1), wh = (win / nw1) % nw1, ww = win % nw1;
+  // position inside the shifted volume -> source token (roll by -shift on D and H only)
+  int d = wd * 4 + (t >> 4), hh = wh * 4 + ((t >> 2) & 3);
+  const int w = ww * 4 + (t & 3);
+  d = (d + shift) % res;
+  hh = (hh + shift) % res;
+  const size_t tok = (((size_t)b * res + d) * res + hh) * res + w;
+  const int C = heads * kHeadDim;
+  const T* src = qkv + tok * 3 * C + h * kHeadDim;
+  float q[kHeadDim];
+  float qn = 0.f, kn = 0.f;
+#pragma unroll
+  for (int i = 0; i < kHeadDim; ++i) {
+    q[i] = ldf(src + i);
+    qn = fmaf(q[i], q[i], qn);
+    const float kv = ldf(src + C + i);
+    ks[t][i] = kv;
+    kn = fmaf(kv, kv, kn);
+    vs[t][i] = ldf(src + 2 * C + i);
+  }
+  // F.normalize(dim=-1, eps=1e-12) on q and k, then the per-head logit scale (folded into q)
+  const float qi = scale[h] / fmaxf(sqrtf(qn), 1e-12f), ki = 1.0f / fmaxf(sqrtf(kn), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < kHeadDim; ++i) {
+    q[i] *= qi;
+    ks[t][i] *= ki;
+  }
+  __syncthreads();
+  float s[kTokens];
+  const float* bias = rel_bias + ((size_t)h * kTokens + t) * kTokens;
+  const float* mk = mask ? mask + ((size_t)win * kTokens + t) * kTokens : nullptr;
+  float mx = -3.0e38f;
+#pragma unroll
+  for (int j = 0; j < kTokens; ++j) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < kHeadDim; ++i) a = fmaf(q[i], ks[j][i], a);
+    a += __ldg(bias + j);
+    if (mk) a += __ldg(mk + j);
+    s[j] = a;
+    mx = fmaxf(mx, a);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kTokens; ++j) {
+    s[j] = __expf(s[j] - mx);
+    sum += s[j];
+  }
+  const float inv = 1.0f / sum;
+  float o[kHeadDim];
+#pragma unroll
+  for (int i = 0; i < kHeadDim; ++i) o[i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < kTokens; ++j) {
+    const float p = s[j] * inv;
+#pragma unroll
+    for (int i = 0; i < kHeadDim; ++i) o[i] = fmaf(p, vs[j][i], o[i]);
+  }
+  T* dst = out + tok * C + h * kHeadDim;
+#pragma unroll
+  for (int i = 0; i < kHeadDim; ++i) stf(dst + i, o[i]);
+}
+
+// one warp per row: y = shortcut + LayerNorm(h) * gamma + beta   (C = 32 * PER)
+template <typename T, int PER>
+__global__ void __launch_bounds__(256) ln_residual_kernel(const float* __restrict__ shortcut, const T* __restrict__ hsrc,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* __restrict__ y, int64_t rows, float eps) {
+  constexpr int C = 32 * PER;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const T* hp = hsrc + row * C;
+  float v[PER];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    v[i] = ldf(hp + lane + 32 * i);
+    sum += v[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const float dlt = v[i] - mean;
+    var = fmaf(dlt, dlt, var);
+  }
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / (float)C + eps);
+  const float* sp = shortcut ? shortcut + row * C : nullptr;
+  float* yp = y + row * C;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int c = lane + 32 * i;
+    float r = (v[i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+    if (sp) r += sp[c];
+    yp[c] = r;
+  }
+}
+
+template <typename T>
+cudaError_t launch_ln(const float* shortcut, const T* h, const float* gamma, const float* beta, float* y, int64_t rows,
+                      int C, float eps, cudaStream_t stream) {
+  const unsigned blocks = (unsigned)((rows + 7) / 8);
+  switch (C / 32) {
+    case 3: ln_residual_kernel<T, 3><<<blocks, 256, 0, stream>>>(shortcut, h, gamma, beta, y, rows, eps); break;
+    case 6: ln_residual_kernel<T, 6><<<blocks, 256, 0, stream>>>(shortcut, h, gamma, beta, y, rows, eps); break;
+    case 12: ln_residual_kernel<T, 12><<<blocks, 256, 0, stream>>>(shortcut, h, gamma, beta, y, rows, eps); break;
+    case 24: ln_residual_kernel<T, 24><<<blocks, 256, 0, stream>>>(shortcut, h, gamma, beta, y, rows, eps); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int pmnet_window_attention(const void* qkv, void* out, const float* logit_scale, const float* rel_bias,
+                           const float* attn_mask, int32_t B, int32_t res, int32_t shift, int32_t heads,
+                           int32_t is_bf16, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!qkv || !out || !logit_scale || !rel_bias) {
+    pmnet_set_error("pmnet_window_attention: null argument");
+    return PMNET_EINVAL;
+  }
+  if (B <= 0 || res < 4 || (res & 3) || heads <= 0 || shift < 0 || shift >= 4) {
+    pmnet_set_error("pmnet_window_attention: resolution must be a multiple of the 4^3 window");
+    return PMNET_EINVAL;
+  }
+  const int nw = (res / 4) * (res / 4) * (res / 4);
+  dim3 grid((unsigned)(B * nw), (unsigned)heads);
+  if (is_bf16)
+    window_attention_kernel<__nv_bfloat16><<<grid, kTokens, 0, stream>>>(
+        (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, logit_scale, rel_bias, attn_mask, res, shift, heads);
+  else
+    window_attention_kernel<float><<<grid, kTokens, 0, stream>>>((const float*)qkv, (float*)out, logit_scale, rel_bias,
+                                                                 attn_mask, res, shift, heads);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    pmnet_set_error(cudaGetErrorString(e));
+    return PMNET_ECUDA;
+  }
+  return PMNET_OK;
+}
+
+int pmnet_ln_residual(const float* shortcut, const void* h, int32_t h_is_bf16, const float* gamma, const float* beta,
+                      float* y, int64_t rows, int32_t C, float eps, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!h || !gamma || !beta || !y) {
+    pmnet_set_error("pmnet_ln_residual: null argument");
+    return PMNET_EINVAL;
+  }
+  if (rows <= 0 || (C != 96 && C != 192 && C != 384 && C != 768)) {
+    pmnet_set_error("pmnet_ln_residual: C must be 96, 192, 384 or 768 (the Swin stage widths)");
+    return PMNET_EINVAL;
+  }
+  cudaError_t e = h_is_bf16 ? launch_ln<__nv_bfloat16>(shortcut, (const __nv_bfloat16*)h, gamma, beta, y, rows, C, eps, stream)
+                            : launch_ln<float>(shortcut, (const float*)h, gamma, beta, y, rows, C, eps, stream);
+  if (e != cudaSuccess) {
+    pmnet_set_error(cudaGetErrorString(e));
+    return PMNET_ECUDA;
+  }
+  return PMNET_OK;
+}
+
+}  // extern "C"

@@ -11,6 +11,7 @@ continuous position bias is 16*sigmoid(cpb_mlp(table)); logit scale clamped at l
 
 from __future__ import annotations
 
+import ctypes as C_
 import math
 
 import torch
@@ -44,6 +45,11 @@ class SwinV2Backbone:
         # LayerNorm / softmax / residuals in fp32) for throughput runs
         self.precision = "fp32"
         self._w16: dict[str, torch.Tensor] = {}
+        # fused = True (default on CUDA): the non-GEMM part of every block runs in two kernels of csrc/swin_ops.cu
+        # (window attention incl. shift / partition / bias / mask / softmax, and LayerNorm + residual);
+        # fused = False is the op-by-op statement of the reference used for CPU checks
+        self.fused = True
+        self._scale_cache: dict[str, torch.Tensor] = {}
 
     def _lin(self, x: torch.Tensor, wname: str, bias: torch.Tensor | None = None) -> torch.Tensor:
         if self.precision == "bf16":
@@ -85,6 +91,8 @@ class SwinV2Backbone:
         return self._lin(out, blk + "attn.proj.weight", self._g(blk + "attn.proj.bias"))
 
     def _block(self, x: torch.Tensor, blk: str, res: int, heads: int, shift: int) -> torch.Tensor:
+        if self.fused and x.is_cuda:
+            return self._block_fused(x, blk, res, heads, shift)
         B, L, C = x.shape
         ws = WINDOW
         if res <= ws:  # swinv2.py:206-209
@@ -103,11 +111,72 @@ class SwinV2Backbone:
         m = self._lin(F.gelu(m), blk + "mlp.fc2.weight", self._g(blk + "mlp.fc2.bias"))
         return x + F.layer_norm(m, (C,), self._g(blk + "norm2.weight"), self._g(blk + "norm2.bias"))
 
+    # ------------------------------------------------------------------ fused path (csrc/swin_ops.cu)
+    def _gemm(self, x: torch.Tensor, wname: str, bias: torch.Tensor | None, keep16: bool = False) -> torch.Tensor:
+        """Plain library GEMM; bf16 operands when precision == 'bf16' (output stays bf16 if keep16)."""
+        if self.precision == "bf16":
+            w = self._w16.get(wname)
+            if w is None:
+                w = self._w16[wname] = self._g(wname).to(torch.bfloat16)
+            b16 = None
+            if bias is not None:
+                b16 = self._w16.get(wname + "#b")
+                if b16 is None:
+                    b16 = self._w16[wname + "#b"] = bias.to(torch.bfloat16)
+            y = F.linear(x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16), w, b16)
+            return y if keep16 else y.float()
+        return F.linear(x, self._g(wname), bias)
+
+    def _ln_res(self, shortcut: torch.Tensor | None, h: torch.Tensor, wname: str, bname: str, out=None) -> torch.Tensor:
+        from . import _lib
+
+        rows, C = h.numel() // h.shape[-1], h.shape[-1]
+        h = h.contiguous()
+        y = out if out is not None else torch.empty(h.shape, dtype=torch.float32, device=h.device)
+        rc = _lib.lib().pmnet_ln_residual(
+            shortcut.data_ptr() if shortcut is not None else None, h.data_ptr(), int(h.dtype == torch.bfloat16),
+            self._g(wname).data_ptr(), self._g(bname).data_ptr(), y.data_ptr(), rows, C, C_.c_float(1e-5),
+            C_.c_void_p(torch.cuda.current_stream(h.device).cuda_stream),
+        )  # fmt: skip
+        _lib.check(rc, "pmnet_ln_residual")
+        return y
+
+    def _block_fused(self, x: torch.Tensor, blk: str, res: int, heads: int, shift: int) -> torch.Tensor:
+        from . import _lib
+
+        B, L, C = x.shape
+        if res <= WINDOW:
+            shift = 0
+        qb, vb = self._g(blk + "attn.q_bias"), self._g(blk + "attn.v_bias")
+        bias = self._scale_cache.get(blk + "qkvb")
+        if bias is None:
+            bias = self._scale_cache[blk + "qkvb"] = torch.cat((qb, torch.zeros_like(vb), vb))
+            self._scale_cache[blk + "scale"] = (
+                torch.clamp(self._g(blk + "attn.logit_scale"), max=math.log(1.0 / 0.01)).exp().reshape(-1).contiguous()
+            )
+        qkv = self._gemm(x, blk + "attn.qkv.weight", bias, keep16=True).contiguous()
+        attn = torch.empty((B, L, C), dtype=qkv.dtype, device=x.device)
+        mask = self.sd.get(self.p + blk + "attn_mask") if shift > 0 else None
+        rc = _lib.lib().pmnet_window_attention(
+            qkv.data_ptr(), attn.data_ptr(), self._scale_cache[blk + "scale"].data_ptr(),
+            self._rel_bias(blk, heads, 64).data_ptr(), mask.data_ptr() if mask is not None else None,
+            B, res, shift, heads, int(qkv.dtype == torch.bfloat16),
+            C_.c_void_p(torch.cuda.current_stream(x.device).cuda_stream),
+        )  # fmt: skip
+        _lib.check(rc, "pmnet_window_attention")
+        proj = self._gemm(attn, blk + "attn.proj.weight", self._g(blk + "attn.proj.bias"), keep16=True)
+        x = self._ln_res(x, proj, blk + "norm1.weight", blk + "norm1.bias")
+        m = self._gemm(x, blk + "mlp.fc1.weight", self._g(blk + "mlp.fc1.bias"), keep16=True)
+        m = self._gemm(F.gelu(m), blk + "mlp.fc2.weight", self._g(blk + "mlp.fc2.bias"), keep16=True)
+        return self._ln_res(x, m, blk + "norm2.weight", blk + "norm2.bias", out=x)
+
     def _merge(self, x: torch.Tensor, pre: str, res: int) -> torch.Tensor:
         B, L, C = x.shape
         x = x.view(B, res, res, res, C)
         parts = [x[:, i::2, j::2, k::2, :] for k in (0, 1) for j in (0, 1) for i in (0, 1)]  # swinv2.py:346-354 order
         x = torch.cat(parts, -1).reshape(B, -1, 8 * C)
+        if self.fused and x.is_cuda:
+            return self._ln_res(None, self._gemm(x, pre + "reduction.weight", None, keep16=True), pre + "norm.weight", pre + "norm.bias")
         x = self._lin(x, pre + "reduction.weight")
         return F.layer_norm(x, (2 * C,), self._g(pre + "norm.weight"), self._g(pre + "norm.bias"))
 
@@ -123,7 +192,10 @@ class SwinV2Backbone:
         for li, (depth, heads) in enumerate(zip(DEPTHS, HEADS)):
             for bi in range(depth):
                 x = self._block(x, f"layers.{li}.blocks.{bi}.", res, heads, 0 if bi % 2 == 0 else WINDOW // 2)
-            o = F.layer_norm(x, (dim,), self._g(f"norm{li}.weight"), self._g(f"norm{li}.bias"))
+            if self.fused and x.is_cuda:
+                o = self._ln_res(None, x, f"norm{li}.weight", f"norm{li}.bias")
+            else:
+                o = F.layer_norm(x, (dim,), self._g(f"norm{li}.weight"), self._g(f"norm{li}.bias"))
             outs.append(o.view(B, res, res, res, dim).permute(0, 4, 1, 2, 3).contiguous())
             if li < len(DEPTHS) - 1:
                 x = self._merge(x, f"layers.{li}.downsample.", res)

@@ -166,3 +166,23 @@ def net_type(t):
     from pharmaconet_b200.constants import INTERACTION_LIST
 
     return INTERACTION_LIST[int(t)]
+
+
+def test_fused_swin_ops_match_op_by_op_path(setup):
+    """csrc/swin_ops.cu (window attention, LayerNorm + residual) against the op-by-op torch statement of the block."""
+    bb = setup["model"].backbone
+    img = setup["image"].cuda()
+    try:
+        bb.fused = False
+        ref = bb.forward(img)
+        bb.fused = True
+        out = bb.forward(img)
+        for a, b in zip(out, ref):
+            assert (a - b).abs().max().item() <= 2e-4 * max(1.0, b.abs().max().item())
+        bb.precision = "bf16"
+        out16 = bb.forward(img)
+        for a, b in zip(out16, ref):
+            rel = ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
+            assert rel <= 3e-2, rel  # bf16 GEMM operands through 12 blocks
+    finally:
+        bb.fused, bb.precision = True, "fp32"
