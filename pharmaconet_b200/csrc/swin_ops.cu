@@ -33,6 +33,46 @@ __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
 template <>
 __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
+// 32 contiguous values of a token-head row, as 128-bit accesses
+__device__ __forceinline__ void load_row32(const float* p, float (&v)[32]) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 t = __ldg(q + i);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void load_row32(const __nv_bfloat16* p, float (&v)[32]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 t = __ldg(q + i);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h[j]);
+      v[8 * i + 2 * j] = f.x;
+      v[8 * i + 2 * j + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void store_row32(float* p, const float (&v)[32]) {
+  float4* q = reinterpret_cast<float4*>(p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void store_row32(__nv_bfloat16* p, const float (&v)[32]) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
+    q[i] = t;
+  }
+}
+
 constexpr int kHeadDim = 32;
 constexpr int kTokens = 64;  // 4^3 window
 
@@ -43,8 +83,8 @@ __global__ void __launch_bounds__(kTokens) window_attention_kernel(const T* __re
                                                                    const float* __restrict__ rel_bias,
                                                                    const float* __restrict__ mask, int res, int shift,
                                                                    int heads) {
-  __shared__ float ks[kTokens][kHeadDim + 1];
-  __shared__ float vs[kTokens][kHeadDim];
+  __shared__ __align__(16) float ks[kTokens][kHeadDim];  // every thread reads the same row: broadcast, no conflicts
+  __shared__ __align__(16) float vs[kTokens][kHeadDim];
   const int t = threadIdx.x, h = blockIdx.y;
   const int nw1 = res / 4, nw = nw1 * nw1 * nw1;
   const int win = blockIdx.x % nw, b = blockIdx.x / nw;
@@ -57,23 +97,23 @@ __global__ void __launch_bounds__(kTokens) window_attention_kernel(const T* __re
   const size_t tok = (((size_t)b * res + d) * res + hh) * res + w;
   const int C = heads * kHeadDim;
   const T* src = qkv + tok * 3 * C + h * kHeadDim;
-  float q[kHeadDim];
+  float q[kHeadDim], kk[kHeadDim], vv[kHeadDim];
+  load_row32(src, q);
+  load_row32(src + C, kk);
+  load_row32(src + 2 * C, vv);
   float qn = 0.f, kn = 0.f;
 #pragma unroll
   for (int i = 0; i < kHeadDim; ++i) {
-    q[i] = ldf(src + i);
     qn = fmaf(q[i], q[i], qn);
-    const float kv = ldf(src + C + i);
-    ks[t][i] = kv;
-    kn = fmaf(kv, kv, kn);
-    vs[t][i] = ldf(src + 2 * C + i);
+    kn = fmaf(kk[i], kk[i], kn);
+    vs[t][i] = vv[i];
   }
   // F.normalize(dim=-1, eps=1e-12) on q and k, then the per-head logit scale (folded into q)
   const float qi = scale[h] / fmaxf(sqrtf(qn), 1e-12f), ki = 1.0f / fmaxf(sqrtf(kn), 1e-12f);
 #pragma unroll
   for (int i = 0; i < kHeadDim; ++i) {
     q[i] *= qi;
-    ks[t][i] *= ki;
+    ks[t][i] = kk[i] * ki;
   }
   __syncthreads();
   float s[kTokens];
@@ -82,9 +122,18 @@ __global__ void __launch_bounds__(kTokens) window_attention_kernel(const T* __re
   float mx = -3.0e38f;
 #pragma unroll
   for (int j = 0; j < kTokens; ++j) {
-    float a = 0.f;
+    // four independent partial sums: the 32-long dot product is otherwise one dependent FMA chain
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float4* kr = reinterpret_cast<const float4*>(ks[j]);
 #pragma unroll
-    for (int i = 0; i < kHeadDim; ++i) a = fmaf(q[i], ks[j][i], a);
+    for (int i = 0; i < kHeadDim / 4; ++i) {
+      const float4 k4 = kr[i];
+      a0 = fmaf(q[4 * i + 0], k4.x, a0);
+      a1 = fmaf(q[4 * i + 1], k4.y, a1);
+      a2 = fmaf(q[4 * i + 2], k4.z, a2);
+      a3 = fmaf(q[4 * i + 3], k4.w, a3);
+    }
+    float a = (a0 + a1) + (a2 + a3);
     a += __ldg(bias + j);
     if (mk) a += __ldg(mk + j);
     s[j] = a;
@@ -103,12 +152,17 @@ __global__ void __launch_bounds__(kTokens) window_attention_kernel(const T* __re
 #pragma unroll
   for (int j = 0; j < kTokens; ++j) {
     const float p = s[j] * inv;
+    const float4* vr = reinterpret_cast<const float4*>(vs[j]);
 #pragma unroll
-    for (int i = 0; i < kHeadDim; ++i) o[i] = fmaf(p, vs[j][i], o[i]);
+    for (int i = 0; i < kHeadDim / 4; ++i) {
+      const float4 v4 = vr[i];
+      o[4 * i + 0] = fmaf(p, v4.x, o[4 * i + 0]);
+      o[4 * i + 1] = fmaf(p, v4.y, o[4 * i + 1]);
+      o[4 * i + 2] = fmaf(p, v4.z, o[4 * i + 2]);
+      o[4 * i + 3] = fmaf(p, v4.w, o[4 * i + 3]);
+    }
   }
-  T* dst = out + tok * C + h * kHeadDim;
-#pragma unroll
-  for (int i = 0; i < kHeadDim; ++i) stf(dst + i, o[i]);
+  store_row32(out + tok * C + h * kHeadDim, o);
 }
 
 // one warp per row: y = shortcut + LayerNorm(h) * gamma + beta   (C = 32 * PER)

@@ -186,7 +186,10 @@ class SwinV2Backbone:
         x = F.conv3d(image, self._g("patch_embed.proj.weight"), self._g("patch_embed.proj.bias"), stride=PATCH)
         B, C = x.shape[0], x.shape[1]
         x = x.flatten(2).transpose(1, 2)
-        x = F.layer_norm(x, (C,), self._g("patch_embed.norm.weight"), self._g("patch_embed.norm.bias"))
+        if self.fused and x.is_cuda:
+            x = self._ln_res(None, x.contiguous(), "patch_embed.norm.weight", "patch_embed.norm.bias")
+        else:
+            x = F.layer_norm(x, (C,), self._g("patch_embed.norm.weight"), self._g("patch_embed.norm.bias"))
         outs = []
         res, dim = self.res0, EMBED
         for li, (depth, heads) in enumerate(zip(DEPTHS, HEADS)):
