@@ -204,3 +204,17 @@ def test_more_than_32_conformers_mixed_batch():
     too_many = LigandBatch.from_typed(synthetic.make_ligands(2, 130, seed=34))
     with pytest.raises(ValueError):
         scoring.score_batch(dm, scoring.DeviceLigandBatch.from_host(too_many, "cuda:0"))
+
+
+def test_ligand_without_pharmacophores_scores_zero():
+    from pharmaconet_b200.ligand import TypedLigand
+
+    c = load_case("syn0_c8")
+    ligs = synthetic.make_ligands(3, 8, seed=40)
+    empty = TypedLigand([6, 8], [[1], [0]], [], np.zeros((2, 8, 3), dtype=np.float32))
+    batch = LigandBatch.from_typed([ligs[0], empty, ligs[1], empty, ligs[2]])
+    out = _run(c["model"], batch, None)
+    o = orc.score(c["model"], batch, None)
+    assert out["scores"][1] == 0.0 and out["scores"][3] == 0.0  # graph_match.py:95-96
+    assert np.array_equal(out["status"], o["status"]) and out["status"][1] == _abi.LIG_EMPTY
+    assert rel_err(out["scores"][[0, 2, 4]], o["scores"][[0, 2, 4]]).max() <= REL_TOL
