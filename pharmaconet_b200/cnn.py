@@ -114,7 +114,9 @@ class PharmacoNetModel:
 
     # ------------------------------------------------------------------ detector.py:36-43
     @torch.no_grad()
-    def forward_feature(self, in_image: torch.Tensor) -> Features:
+    def forward_feature(self, in_image: torch.Tensor, nchw: bool = True) -> Features:
+        """nchw=False skips the fp32 NCDHW copies of the five maps (100 MB per pocket at 64^3) and returns the bf16
+        chunked tensors themselves - enough for the other three entry points of this class."""
         image = in_image.to(self.device, torch.float32).contiguous()
         bottom_up = [image, *self.backbone.forward(image)]
         # FPNDecoder.forward (decoders/fpn_decoder.py:86-115), top (4^3) to bottom (64^3)
@@ -128,12 +130,16 @@ class PharmacoNetModel:
             for layer in self.fpn_convs[level]:
                 fpn = self._k3(fpn, layer)[0]
             outs.append(fpn)
-        nchw = []
+        if not nchw:
+            feats = Features(outs)
+            feats.c8 = outs
+            return feats
+        full = []
         for o in outs:
             t = conv.from_c8(o)
             t._pm_c8 = o  # the bf16 chunked twin travels with the tensor: later stages skip the conversion
-            nchw.append(t)
-        feats = Features(nchw)
+            full.append(t)
+        feats = Features(full)
         feats.c8 = outs
         return feats
 
@@ -163,31 +169,28 @@ class PharmacoNetModel:
     def forward_token_prediction(self, features, tokens_list: Sequence[torch.Tensor]):
         sd = self.sd
         x = self._as_c8(features)
-        scores, feats = [], []
-        for b, tokens in enumerate(tokens_list):
-            tokens = tokens.to(self.device, torch.long)
-            if tokens.shape[0] == 0:
-                tf = torch.empty((0, 192), dtype=torch.float32, device=self.device)
-            else:
-                xs, ys, zs, it = tokens.unbind(1)
-                voxel = x[b][:, xs, ys, zs, :].permute(1, 0, 2).reshape(-1, 96).float()
-                h0 = torch.cat([voxel, sd["token_head.interaction_embedding.weight"][it]], dim=1)
-                skip = (
-                    F.linear(h0, sd["token_head.skip.weight"], sd["token_head.skip.bias"])
-                    if "token_head.skip.weight" in sd
-                    else h0
-                )
-                h = h0
-                for i in (0, 2, 4):
-                    h = F.silu(F.linear(h, sd[f"token_head.feature_mlp.{i}.weight"], sd[f"token_head.feature_mlp.{i}.bias"]))
-                tf = skip + h
-            s = tf
-            for i in (0, 2):
-                s = torch.relu(F.linear(s, sd[f"token_head.score_mlp.{i}.weight"], sd[f"token_head.score_mlp.{i}.bias"]))
-            s = F.linear(s, sd["token_head.score_mlp.4.weight"], sd["token_head.score_mlp.4.bias"]).squeeze(-1)
-            scores.append(s)
-            feats.append(tf)
-        return scores, feats
+        toks = [t.to(self.device, torch.long) for t in tokens_list]
+        counts = [int(t.shape[0]) for t in toks]
+        if sum(counts) == 0:
+            return (
+                [torch.empty((0,), dtype=torch.float32, device=self.device) for _ in toks],
+                [torch.empty((0, 192), dtype=torch.float32, device=self.device) for _ in toks],
+            )
+        # all pockets' tokens through the MLPs at once (the reference loops over images, token_head.py:62-66)
+        allt = torch.cat(toks, 0)
+        bidx = torch.repeat_interleave(torch.arange(len(toks), device=self.device), torch.tensor(counts, device=self.device))
+        voxel = x[bidx, :, allt[:, 0], allt[:, 1], allt[:, 2], :].reshape(-1, 96).float()
+        h0 = torch.cat([voxel, sd["token_head.interaction_embedding.weight"][allt[:, 3]]], dim=1)
+        skip = F.linear(h0, sd["token_head.skip.weight"], sd["token_head.skip.bias"]) if "token_head.skip.weight" in sd else h0
+        h = h0
+        for i in (0, 2, 4):
+            h = F.silu(F.linear(h, sd[f"token_head.feature_mlp.{i}.weight"], sd[f"token_head.feature_mlp.{i}.bias"]))
+        tf = skip + h
+        s = tf
+        for i in (0, 2):
+            s = torch.relu(F.linear(s, sd[f"token_head.score_mlp.{i}.weight"], sd[f"token_head.score_mlp.{i}.bias"]))
+        s = F.linear(s, sd["token_head.score_mlp.4.weight"], sd["token_head.score_mlp.4.bias"]).squeeze(-1)
+        return list(torch.split(s, counts)), list(torch.split(tf, counts))
 
     # ------------------------------------------------------------------ detector.py:73-91, mask_head.py:38-196
     def _shared_laterals(self, features, b: int):

@@ -148,14 +148,14 @@ class PharmacoNet:
 
     # ------------------------------------------------------------------ shared front part
     @torch.no_grad()
-    def _features_and_hotspots(self, protein_data):
+    def _features_and_hotspots(self, protein_data, nchw: bool = True):
         image, mask, token_pos, tokens = protein_data
         dev = self.device
         image = image.to(dev, torch.float32)
         token_pos = token_pos.to(dev, torch.float32)
         tokens = tokens.to(dev, torch.long)
         mask = mask.to(dev, torch.bool)
-        feats = self.model.forward_feature(image.unsqueeze(0))
+        feats = self.model.forward_feature(image.unsqueeze(0), nchw=nchw)
         scores, tfeat = self.model.forward_token_prediction(feats[-1], [tokens])
         abs_scores = scores[0].sigmoid()
         narrow, wide = self.model.forward_cavity_extraction(feats[-1])
@@ -214,7 +214,7 @@ class PharmacoNet:
     @torch.no_grad()
     def create_density_maps(self, protein_data) -> list[HotspotInfo]:
         self.print_log("debug", f"Protein-based Pharmacophore Modeling... (device: {self.device})")
-        r = self._features_and_hotspots(protein_data)
+        r = self._features_and_hotspots(protein_data, nchw=False)  # the maps stay in the kernels' layout
         hotspots, feats = r["hotspots"], r["feats"]
         logits = []
         if hotspots.shape[0] > 0:

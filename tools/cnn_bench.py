@@ -48,7 +48,7 @@ def stage_times():
     out = {}
     out["backbone"] = timed(lambda: model.backbone.forward(images), a.iters)
     feats = model.forward_feature(images)
-    out["forward_feature"] = timed(lambda: model.forward_feature(images), a.iters)
+    out["forward_feature"] = timed(lambda: model.forward_feature(images, nchw=False), a.iters)
     out["cavity"] = timed(lambda: model.forward_cavity_extraction(feats[-1]), a.iters)
     out["token"] = timed(lambda: model.forward_token_prediction(feats[-1], [tokens] * a.chunk), a.iters)
     return out, feats
