@@ -13,6 +13,7 @@ from __future__ import annotations
 import ctypes as C
 from collections.abc import Sequence
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -235,21 +236,27 @@ class PharmacoNetModel:
                 raise NotImplementedError("groups of more than 4 boxes are not supported by the combine kernel")
             tfeat = tfeat.to(self.device, torch.float32)
             shared = self._shared_laterals(multi_scale_features, b)
-            member = (torch.arange(nbox, device=self.device) // gs) * gs  # first box of each box's group
+            # token voxels of every box's group, per level, built on the host in one go (tokens are a few dozen
+            # rows): pvox_levels[level][j, k] = flat voxel of the k-th member of box j's group, -1 when absent
+            tok_np = tokens.cpu().numpy()
+            member = (np.arange(nbox) // gs) * gs
+            src = member[:, None] + np.arange(4)[None, :]
+            ok = (np.arange(4)[None, :] < gs) & (src < nbox)
+            src = np.where(ok, src, 0)
+            pv = np.empty((5, nbox, 4), dtype=np.int32)
+            for level in range(5):
+                D = shared[level].shape[1]
+                div = size // D
+                vox = ((tok_np[:, 0] // div) * D + tok_np[:, 1] // div) * D + tok_np[:, 2] // div
+                pv[level] = np.where(ok, vox[src], -1)
+            pvox_levels = torch.from_numpy(pv).to(self.device)
             pieces = []
             for lo in range(0, nbox, 48):  # bound the per-call activation memory (48 boxes x 50 MB at 64^3)
                 hi = min(nbox, lo + 48)
                 fpn = None
                 for level in (4, 3, 2, 1, 0):
                     s = shared[level]
-                    D = s.shape[1]
-                    div = size // D
-                    vox = ((tokens[:, 0] // div) * D + tokens[:, 1] // div) * D + tokens[:, 2] // div
-                    pvox = torch.full((hi - lo, 4), -1, dtype=torch.int32, device=self.device)
-                    for k in range(gs):
-                        src = member[lo:hi] + k
-                        ok = src < nbox
-                        pvox[ok, k] = vox[src[ok]].to(torch.int32)
+                    pvox = pvox_levels[level, lo:hi].contiguous()
                     bg = F.linear(tfeat[lo:hi], sd[f"mask_head.background_mlp_list.{level}.weight"], sd[f"mask_head.background_mlp_list.{level}.bias"])
                     pt = F.linear(tfeat[lo:hi], sd[f"mask_head.point_mlp_list.{level}.weight"], sd[f"mask_head.point_mlp_list.{level}.bias"])
                     lat = self.mask_lateral[level]
