@@ -73,11 +73,11 @@ def conv3d_k3_c96(
         y = torch.empty_like(x_c8) if store_out else None
         head = torch.empty((B, D, H, W), dtype=torch.float32, device=dev) if head_w is not None else None
         if planes_per_item <= 0:
-            # >= 8 work items per CTA when the problem allows it (static round-robin: keeps the last wave short);
-            # every item re-loads 2 halo planes, so items are not made shorter than 8 planes
+            # >= 4 work items per CTA when the problem allows it (static round-robin: keeps the last wave short);
+            # every item re-loads 2 halo planes and refills the pipeline, so items are not made shorter than 8 planes
             tiles = B * -(-H // 16) * -(-W // 8)
             planes_per_item = D
-            while planes_per_item > 8 and tiles * (D // planes_per_item) < 8 * 148:
+            while planes_per_item > 8 and tiles * (D // planes_per_item) < 4 * 148:
                 planes_per_item //= 2
             planes_per_item = max(2, planes_per_item)
         rc = L.pmnet_conv3d_k3_c96(
