@@ -168,6 +168,17 @@ __device__ __forceinline__ int rec_model_node(uint2 r, int a, const uint8_t* __r
   return (a < 4) ? (int)((r.y >> (8 * a)) & 255u) : (int)mlist[(r.x >> 16) + a];
 }
 
+template <int W>
+__device__ __forceinline__ void eval_edge(const float4 e, const float (&d)[W], float (&lik)[W], int (&npass)[W]) {
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    const float s = __fmul_rn(__fsub_rn(d[w], e.x), e.y);
+    const float s2 = __fmul_rn(s, s);
+    lik[w] = fmaf(e.w, gauss(s2), lik[w]);
+    npass[w] += (s2 < 4.0f) ? 1 : 0;
+  }
+}
+
 // One ligand-node pair against two matched model-node lists (match_utils_numba.py:67-86) for the W conformers of a
 // lane: adds likelihood / (M*N) to sc[] and counts the conformers failing the "half of the pairs within 2 sigma" test.
 template <int W>
@@ -192,17 +203,23 @@ __device__ __forceinline__ void pair_term(const SmemModel& sm, const uint8_t* __
     npass[w] = 0;
     lik[w] = 0.0f;
   }
-  for (int a = 0; a < M; ++a) {
-    const float4* row = sm.edge + rec_model_node(r1, a, mlist) * sm.nm;
-    for (int b = 0; b < N; ++b) {
-      const float4 e = row[rec_model_node(r2, b, mlist)];
+  if (M <= 4 && N <= 4) {
+    // the common multi-node case, fully unrolled: model nodes come out of the record words with constant shifts and
+    // the (warp-uniform) bounds only skip blocks
 #pragma unroll
-      for (int w = 0; w < W; ++w) {
-        const float s = __fmul_rn(__fsub_rn(d[w], e.x), e.y);
-        const float s2 = __fmul_rn(s, s);
-        lik[w] = fmaf(e.w, gauss(s2), lik[w]);
-        npass[w] += (s2 < 4.0f) ? 1 : 0;
+    for (int a = 0; a < 4; ++a) {
+      if (a < M) {
+        const float4* row = sm.edge + ((r1.y >> (8 * a)) & 255u) * sm.nm;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (b < N) eval_edge<W>(row[(r2.y >> (8 * b)) & 255u], d, lik, npass);
+        }
       }
+    }
+  } else {
+    for (int a = 0; a < M; ++a) {
+      const float4* row = sm.edge + rec_model_node(r1, a, mlist) * sm.nm;
+      for (int b = 0; b < N; ++b) eval_edge<W>(row[rec_model_node(r2, b, mlist)], d, lik, npass);
     }
   }
   const int mn = M * N;
