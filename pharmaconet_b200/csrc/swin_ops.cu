@@ -26,13 +26,6 @@ template <>
 __device__ __forceinline__ float ldf<float>(const float* p) { return __ldg(p); }
 template <>
 __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
-template <typename T>
-__device__ __forceinline__ void stf(T* p, float v);
-template <>
-__device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
-template <>
-__device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
-
 // 32 contiguous values of a token-head row, as 128-bit accesses
 __device__ __forceinline__ void load_row32(const float* p, float (&v)[32]) {
   const float4* q = reinterpret_cast<const float4*>(p);
@@ -60,17 +53,6 @@ __device__ __forceinline__ void store_row32(float* p, const float (&v)[32]) {
   float4* q = reinterpret_cast<float4*>(p);
 #pragma unroll
   for (int i = 0; i < 8; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
-__device__ __forceinline__ void store_row32(__nv_bfloat16* p, const float (&v)[32]) {
-  uint4* q = reinterpret_cast<uint4*>(p);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 t;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
-    q[i] = t;
-  }
 }
 
 constexpr int kHeadDim = 32;
@@ -165,6 +147,155 @@ __global__ void __launch_bounds__(kTokens) window_attention_kernel(const T* __re
   store_row32(out + tok * C + h * kHeadDim, o);
 }
 
+
+// ------------------------------------------------------------------ tensor-core version for bf16 storage
+// One warp per (window, head): S = Q K^T (64 x 64 x 32) and O = P V (64 x 32 x 64) with mma.sync m16n8k16 (bf16 in,
+// fp32 accumulate), 16 query rows at a time so that S stays in 32 registers; P is re-used from the accumulator
+// registers as the A operand of the second product. (tcgen05 needs M >= 64 tiles resident in TMEM and a
+// TMEM round trip for the softmax; for 64-token windows that is slower than staying in registers.)
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+constexpr int kQStride = 20;  // words per Q/K row (16 data + 4 pad: conflict-free fragment reads)
+constexpr int kVStride = 36;  // words per V^T row (32 data + 4 pad)
+
+__global__ void __launch_bounds__(32) window_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                  __nv_bfloat16* __restrict__ out,
+                                                                  const float* __restrict__ scale,
+                                                                  const float* __restrict__ rel_bias,
+                                                                  const float* __restrict__ mask, int res, int shift,
+                                                                  int heads) {
+  __shared__ uint32_t Qs[kTokens * kQStride];
+  __shared__ uint32_t Ks[kTokens * kQStride];
+  __shared__ uint32_t Vt[kHeadDim * kVStride];
+  __shared__ unsigned long long tok_of[kTokens];
+  const int lane = threadIdx.x, h = blockIdx.y;
+  const int nw1 = res / 4, nw = nw1 * nw1 * nw1;
+  const int win = blockIdx.x % nw, b = blockIdx.x / nw;
+  const int wd = win / (nw1 * nw1), wh = (win / nw1) % nw1, ww = win % nw1;
+  const int C = heads * kHeadDim;
+  __nv_bfloat16* vt16 = reinterpret_cast<__nv_bfloat16*>(Vt);
+  // ---- load, normalise q and k (fp32), stage as bf16; lane handles tokens lane and lane + 32
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int t = lane + 32 * half;
+    int d = wd * 4 + (t >> 4), hh = wh * 4 + ((t >> 2) & 3);
+    const int w = ww * 4 + (t & 3);
+    d = (d + shift) % res;
+    hh = (hh + shift) % res;
+    const size_t tok = (((size_t)b * res + d) * res + hh) * res + w;
+    tok_of[t] = tok;
+    const __nv_bfloat16* src = qkv + tok * 3 * C + h * kHeadDim;
+    float q[kHeadDim], kk[kHeadDim], vv[kHeadDim];
+    load_row32(src, q);
+    load_row32(src + C, kk);
+    load_row32(src + 2 * C, vv);
+    float qn = 0.f, kn = 0.f;
+#pragma unroll
+    for (int i = 0; i < kHeadDim; ++i) {
+      qn = fmaf(q[i], q[i], qn);
+      kn = fmaf(kk[i], kk[i], kn);
+    }
+    const float qi = 1.0f / fmaxf(sqrtf(qn), 1e-12f), ki = 1.0f / fmaxf(sqrtf(kn), 1e-12f);
+#pragma unroll
+    for (int i = 0; i < kHeadDim / 2; ++i) {
+      Qs[t * kQStride + i] = pack_bf16(q[2 * i] * qi, q[2 * i + 1] * qi);
+      Ks[t * kQStride + i] = pack_bf16(kk[2 * i] * ki, kk[2 * i + 1] * ki);
+    }
+#pragma unroll
+    for (int i = 0; i < kHeadDim; ++i) vt16[i * (2 * kVStride) + t] = __float2bfloat16_rn(vv[i]);
+  }
+  __syncwarp();
+  const int g = lane >> 2, tq = lane & 3;
+  const float sc = scale[h];
+#pragma unroll 1
+  for (int mt = 0; mt < 4; ++mt) {
+    const int r0 = 16 * mt + g, r1 = r0 + 8;
+    float S[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) S[nt][0] = S[nt][1] = S[nt][2] = S[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const uint32_t a0 = Qs[r0 * kQStride + ks * 8 + tq], a1 = Qs[r1 * kQStride + ks * 8 + tq];
+      const uint32_t a2 = Qs[r0 * kQStride + ks * 8 + 4 + tq], a3 = Qs[r1 * kQStride + ks * 8 + 4 + tq];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const uint32_t b0 = Ks[(8 * nt + g) * kQStride + ks * 8 + tq], b1 = Ks[(8 * nt + g) * kQStride + ks * 8 + 4 + tq];
+        mma16816(S[nt], a0, a1, a2, a3, b0, b1);
+      }
+    }
+    // logits = scale * cos + bias (+ mask); row maxima
+    const float* bias0 = rel_bias + ((size_t)h * kTokens + r0) * kTokens + 2 * tq;
+    const float* bias1 = rel_bias + ((size_t)h * kTokens + r1) * kTokens + 2 * tq;
+    const float* m0 = mask ? mask + ((size_t)win * kTokens + r0) * kTokens + 2 * tq : nullptr;
+    const float* m1 = mask ? mask + ((size_t)win * kTokens + r1) * kTokens + 2 * tq : nullptr;
+    float mx0 = -3.0e38f, mx1 = -3.0e38f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float2 bz0 = __ldg(reinterpret_cast<const float2*>(bias0 + 8 * nt));
+      const float2 bz1 = __ldg(reinterpret_cast<const float2*>(bias1 + 8 * nt));
+      S[nt][0] = fmaf(S[nt][0], sc, bz0.x);
+      S[nt][1] = fmaf(S[nt][1], sc, bz0.y);
+      S[nt][2] = fmaf(S[nt][2], sc, bz1.x);
+      S[nt][3] = fmaf(S[nt][3], sc, bz1.y);
+      if (mask) {
+        const float2 k0 = __ldg(reinterpret_cast<const float2*>(m0 + 8 * nt));
+        const float2 k1 = __ldg(reinterpret_cast<const float2*>(m1 + 8 * nt));
+        S[nt][0] += k0.x; S[nt][1] += k0.y; S[nt][2] += k1.x; S[nt][3] += k1.y;
+      }
+      mx0 = fmaxf(mx0, fmaxf(S[nt][0], S[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(S[nt][2], S[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      S[nt][0] = __expf(S[nt][0] - mx0); S[nt][1] = __expf(S[nt][1] - mx0);
+      S[nt][2] = __expf(S[nt][2] - mx1); S[nt][3] = __expf(S[nt][3] - mx1);
+      sum0 += S[nt][0] + S[nt][1];
+      sum1 += S[nt][2] + S[nt][3];
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    // O = P V with the un-normalised probabilities, normalised at the end
+    float O[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) O[nt][0] = O[nt][1] = O[nt][2] = O[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t a0 = pack_bf16(S[2 * ks][0], S[2 * ks][1]), a1 = pack_bf16(S[2 * ks][2], S[2 * ks][3]);
+      const uint32_t a2 = pack_bf16(S[2 * ks + 1][0], S[2 * ks + 1][1]), a3 = pack_bf16(S[2 * ks + 1][2], S[2 * ks + 1][3]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const uint32_t b0 = Vt[(8 * nt + g) * kVStride + ks * 8 + tq], b1 = Vt[(8 * nt + g) * kVStride + ks * 8 + 4 + tq];
+        mma16816(O[nt], a0, a1, a2, a3, b0, b1);
+      }
+    }
+    const float i0 = 1.0f / sum0, i1 = 1.0f / sum1;
+    __nv_bfloat16* d0 = out + tok_of[r0] * C + h * kHeadDim + 2 * tq;
+    __nv_bfloat16* d1 = out + tok_of[r1] * C + h * kHeadDim + 2 * tq;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      *reinterpret_cast<uint32_t*>(d0 + 8 * nt) = pack_bf16(O[nt][0] * i0, O[nt][1] * i0);
+      *reinterpret_cast<uint32_t*>(d1 + 8 * nt) = pack_bf16(O[nt][2] * i1, O[nt][3] * i1);
+    }
+  }
+}
+
 // one warp per row: y = shortcut + LayerNorm(h) * gamma + beta   (C = 32 * PER)
 template <typename T, int PER>
 __global__ void __launch_bounds__(256) ln_residual_kernel(const float* __restrict__ shortcut, const T* __restrict__ hsrc,
@@ -235,9 +366,9 @@ int pmnet_window_attention(const void* qkv, void* out, const float* logit_scale,
   }
   const int nw = (res / 4) * (res / 4) * (res / 4);
   dim3 grid((unsigned)(B * nw), (unsigned)heads);
-  if (is_bf16)
-    window_attention_kernel<__nv_bfloat16><<<grid, kTokens, 0, stream>>>(
-        (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, logit_scale, rel_bias, attn_mask, res, shift, heads);
+  if (is_bf16)  // bf16 storage: tensor-core kernel; fp32 storage: the CUDA-core kernel keeps fp32 parity
+    window_attention_mma_kernel<<<grid, 32, 0, stream>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, logit_scale,
+                                                         rel_bias, attn_mask, res, shift, heads);
   else
     window_attention_kernel<float><<<grid, kTokens, 0, stream>>>((const float*)qkv, (float*)out, logit_scale, rel_bias,
                                                                  attn_mask, res, shift, heads);
