@@ -38,10 +38,13 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return p;
 }
 
-constexpr int kLateralTiles = 4;
+constexpr int kLatVox = 128;   // voxels per block tile
+constexpr int kLatTiles = 4;   // tiles per block (the weight tile is loaded once per 512 voxels)
 
 // ------------------------------------------------------------------ lateral 1x1 conv
-// grid: (ceil(V / 64), B); block 128 = 64 voxels x 2 halves of 48 output channels. Weights [C_in][96] fp32 in smem.
+// grid: (ceil(V / 512), B); block 128 = 4 warps. Warp q owns output channels [24 q, 24 q + 24), lane l owns voxels
+// l, l + 32, l + 64, l + 96 of the tile: 96 accumulators per thread, and every weight float4 read from shared memory
+// (a warp-wide broadcast) feeds 16 FMAs. Weights [C_in][96] fp32 in smem.
 template <int IN_C8>
 __global__ void __launch_bounds__(128) lateral_kernel(const void* __restrict__ x, int cin, const float* __restrict__ wt,
                                                       const float* __restrict__ scale, const float* __restrict__ bias,
@@ -52,79 +55,102 @@ __global__ void __launch_bounds__(128) lateral_kernel(const void* __restrict__ x
   for (int i = threadIdx.x; i < cin * 96; i += blockDim.x) sw[i] = wt[i];
   __syncthreads();
   const int b = blockIdx.y;
-  const int half = threadIdx.x >> 6;
+  const int lane = threadIdx.x & 31, quarter = threadIdx.x >> 5;
   const int Vu = (D / 2) * (H / 2) * (W / 2);
-  // kLateralTiles tiles of 64 voxels per block, so that the weight tile is loaded once per 1024 voxels
-  for (int tile = 0; tile < kLateralTiles; ++tile) {
-    const int v = (blockIdx.x * kLateralTiles + tile) * 64 + (threadIdx.x & 63);
-    if (v >= V) break;
-    float acc[48];
+  for (int tile = 0; tile < kLatTiles; ++tile) {
+    const int v0 = (blockIdx.x * kLatTiles + tile) * kLatVox;
+    if (v0 >= V) break;
+    float acc[4][24];
 #pragma unroll
-    for (int c = 0; c < 48; ++c) acc[c] = 0.0f;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 24; ++c) acc[i][c] = 0.0f;
     if (IN_C8) {
-      const uint4* xp = reinterpret_cast<const uint4*>(x) + (size_t)b * (cin / 8) * V + v;
-      const int nq = cin / 8;
-      uint4 nxt = __ldg(xp);
-      for (int q = 0; q < nq; ++q) {
-        float f[8];
-        unpack8(nxt, f);
-        if (q + 1 < nq) nxt = __ldg(xp + (size_t)(q + 1) * V);  // next chunk in flight during the FMAs
+      const uint4* xp = reinterpret_cast<const uint4*>(x) + (size_t)b * (cin / 8) * V;
+      for (int q = 0; q < cin / 8; ++q) {
+        float f[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int v = v0 + lane + 32 * i;
+          if (v < V) {
+            unpack8(__ldg(xp + (size_t)q * V + v), f[i]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[i][j] = 0.0f;
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4* wr = reinterpret_cast<const float4*>(sw + (q * 8 + j) * 96 + half * 48);
+          const float4* wr = reinterpret_cast<const float4*>(sw + (q * 8 + j) * 96 + quarter * 24);
 #pragma unroll
-          for (int c4 = 0; c4 < 12; ++c4) {
+          for (int c4 = 0; c4 < 6; ++c4) {
             const float4 w4 = wr[c4];
-            acc[4 * c4 + 0] = fmaf(f[j], w4.x, acc[4 * c4 + 0]);
-            acc[4 * c4 + 1] = fmaf(f[j], w4.y, acc[4 * c4 + 1]);
-            acc[4 * c4 + 2] = fmaf(f[j], w4.z, acc[4 * c4 + 2]);
-            acc[4 * c4 + 3] = fmaf(f[j], w4.w, acc[4 * c4 + 3]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              acc[i][4 * c4 + 0] = fmaf(f[i][j], w4.x, acc[i][4 * c4 + 0]);
+              acc[i][4 * c4 + 1] = fmaf(f[i][j], w4.y, acc[i][4 * c4 + 1]);
+              acc[i][4 * c4 + 2] = fmaf(f[i][j], w4.z, acc[i][4 * c4 + 2]);
+              acc[i][4 * c4 + 3] = fmaf(f[i][j], w4.w, acc[i][4 * c4 + 3]);
+            }
           }
         }
       }
     } else {
-      const float* xp = reinterpret_cast<const float*>(x) + (size_t)b * cin * V + v;
-      for (int k0 = 0; k0 < cin; k0 += 8) {
-        float xv[8];
+      const float* xp = reinterpret_cast<const float*>(x) + (size_t)b * cin * V;
+      for (int k0 = 0; k0 < cin; k0 += 4) {
+        float xv[4][4];  // [channel of the group][voxel]: 16 independent loads in flight
 #pragma unroll
-        for (int j = 0; j < 8; ++j) xv[j] = (k0 + j < cin) ? __ldg(xp + (size_t)(k0 + j) * V) : 0.0f;  // 8 loads in flight
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+          for (int i = 0; i < 4; ++i) {
+            const int v = v0 + lane + 32 * i;
+            xv[j][i] = (k0 + j < cin && v < V) ? __ldg(xp + (size_t)(k0 + j) * V + v) : 0.0f;
+          }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
           if (k0 + j < cin) {
-            const float4* wr = reinterpret_cast<const float4*>(sw + (k0 + j) * 96 + half * 48);
+            const float4* wr = reinterpret_cast<const float4*>(sw + (k0 + j) * 96 + quarter * 24);
 #pragma unroll
-            for (int c4 = 0; c4 < 12; ++c4) {
+            for (int c4 = 0; c4 < 6; ++c4) {
               const float4 w4 = wr[c4];
-              acc[4 * c4 + 0] = fmaf(xv[j], w4.x, acc[4 * c4 + 0]);
-              acc[4 * c4 + 1] = fmaf(xv[j], w4.y, acc[4 * c4 + 1]);
-              acc[4 * c4 + 2] = fmaf(xv[j], w4.z, acc[4 * c4 + 2]);
-              acc[4 * c4 + 3] = fmaf(xv[j], w4.w, acc[4 * c4 + 3]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                acc[i][4 * c4 + 0] = fmaf(xv[j][i], w4.x, acc[i][4 * c4 + 0]);
+                acc[i][4 * c4 + 1] = fmaf(xv[j][i], w4.y, acc[i][4 * c4 + 1]);
+                acc[i][4 * c4 + 2] = fmaf(xv[j][i], w4.z, acc[i][4 * c4 + 2]);
+                acc[i][4 * c4 + 3] = fmaf(xv[j][i], w4.w, acc[i][4 * c4 + 3]);
+              }
             }
           }
         }
       }
     }
-    const int w = v % W, h = (v / W) % H, d = v / (W * H);
-    const int vu = ((d >> 1) * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1);
 #pragma unroll
-    for (int q = 0; q < 6; ++q) {
-      const int chunk = half * 6 + q;
-      float y[8];
+    for (int i = 0; i < 4; ++i) {
+      const int v = v0 + lane + 32 * i;
+      if (v >= V) continue;
+      const int w = v % W, h = (v / W) % H, d = v / (W * H);
+      const int vu = ((d >> 1) * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = chunk * 8 + j;
-        float t = acc[q * 8 + j];
-        if (scale) t = fmaf(t, __ldg(scale + c), __ldg(bias + c));
-        if (relu) t = fmaxf(t, 0.0f);
-        y[j] = t;
+      for (int q = 0; q < 3; ++q) {
+        const int chunk = quarter * 3 + q;
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = chunk * 8 + j;
+          float t = acc[i][q * 8 + j];
+          if (scale) t = fmaf(t, __ldg(scale + c), __ldg(bias + c));
+          if (relu) t = fmaxf(t, 0.0f);
+          y[j] = t;
+        }
+        if (up) {
+          float u[8];
+          unpack8(__ldg(up + ((size_t)b * 12 + chunk) * Vu + vu), u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] += u[j];
+        }
+        out[((size_t)b * 12 + chunk) * V + v] = pack8(y);
       }
-      if (up) {
-        float u[8];
-        unpack8(__ldg(up + ((size_t)b * 12 + chunk) * Vu + vu), u);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] += u[j];
-      }
-      out[((size_t)b * 12 + chunk) * V + v] = pack8(y);
     }
   }
 }
@@ -249,7 +275,7 @@ int pmnet_lateral_c96(const void* x, int32_t x_is_c8, int32_t c_in, const float*
     return PMNET_ELIMIT;
   }
   const int V = D * H * W;
-  dim3 grid((V + 64 * kLateralTiles - 1) / (64 * kLateralTiles), B);
+  dim3 grid((V + kLatVox * kLatTiles - 1) / (kLatVox * kLatTiles), B);
   cudaError_t e;
   if (x_is_c8) {
     e = cudaFuncSetAttribute(lateral_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
