@@ -16,8 +16,8 @@
 // UMMA matrix: 8 consecutive w voxels are one 128 B core matrix, SBO = 160 B (next h row), LBO = 2880 B (next
 // chunk) - shifted windows need no data movement. A persistent CTA marches along d: every input plane is loaded once
 // per (h, w) tile column and lives in a 4-slot ring; two consecutive output planes share every weight tap
-// (G = 2) to halve the weight stream from L2. Warp roles: warp 0 TMA producer, warp 1 MMA issuer (one thread),
-// warps 2-5 epilogue (TMEM -> registers -> scale/bias/ReLU -> bf16 -> global). Accumulators are double buffered in
+// (G = 2) to halve the weight stream from L2. Warp roles: warp 0 TMA producer, warps 1-2 MMA issuers (one thread
+// each, one output plane each), warps 3-6 epilogue (TMEM -> registers -> scale/bias/ReLU -> bf16 -> global). Accumulators are double buffered in
 // TMEM (4 x 128 columns) so the epilogue of a plane pair overlaps the MMAs of the next.
 
 #include <cuda.h>
@@ -41,7 +41,7 @@ constexpr int kTapBytes = kChunks * kC * 16;                 // 18432: weights o
 constexpr int kWStages = 4;
 constexpr int kTaps = 27;
 constexpr int kKSteps = kC / 16;                             // 6 MMAs (K = 16) per tap and accumulator
-constexpr int kThreads = 192;
+constexpr int kThreads = 224;  // TMA producer, 2 MMA issuers, 4 epilogue warps
 constexpr uint32_t kTmemCols = 512;                          // 2 buffers x 2 planes x 128-column slots
 
 constexpr int kSmemPlanes = 0;
@@ -177,14 +177,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_k3_c96_kernel(const __grid
   if (threadIdx.x == 0) {
     for (int i = 0; i < kPlaneSlots; ++i) {
       mbar_init(bar(BAR_PFULL + i), 1);
-      mbar_init(bar(BAR_PEMPTY + i), 1);
+      mbar_init(bar(BAR_PEMPTY + i), 2);  // both MMA issuers
     }
     for (int i = 0; i < kWStages; ++i) {
       mbar_init(bar(BAR_WFULL + i), 1);
-      mbar_init(bar(BAR_WEMPTY + i), 1);
+      mbar_init(bar(BAR_WEMPTY + i), 2);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar(BAR_AFULL + i), 1);
+      mbar_init(bar(BAR_AFULL + i), 2);   // both MMA issuers
       mbar_init(bar(BAR_AEMPTY + i), 4);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -233,9 +233,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_k3_c96_kernel(const __grid
         }
       }
     }
-  } else if (warp == 1) {
-    // =============================================================== MMA issuer (one thread)
+  } else if (warp == 1 || warp == 2) {
+    // =============================================================== MMA issuers: warp 1 -> output plane d0 (g = 0),
+    // warp 2 -> output plane d0 + 1 (g = 1); one thread each. Two issuers because one thread cannot feed the tensor
+    // pipe: per tap it pays a barrier poll (~90 cycles), a fence, a commit and ~30 cycles per MMA for 12 MMAs of 48.
     if (lane == 0) {
+      const int g = warp - 1;
       uint32_t pseq0 = 0;  // sequence number of plane (d_begin - 1) of the current item
       uint32_t wseq = 0, gseq = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -245,6 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_k3_c96_kernel(const __grid
           const uint32_t s = plane_seq(d);
           mbar_wait(bar(BAR_PFULL + s % kPlaneSlots), (s / kPlaneSlots) & 1);
         };
+        // a plane slot is free again when BOTH issuers have retired their last MMA on it (barrier count 2)
         auto release_plane = [&](int d) { tc_commit(bar(BAR_PEMPTY + plane_seq(d) % kPlaneSlots)); };
         for (int d0 = it.d_begin; d0 < it.d_end; d0 += 2, ++gseq) {
           const uint32_t buf = gseq & 1;
@@ -254,20 +258,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_k3_c96_kernel(const __grid
           // window by a tap or a K step is one 32-bit add with an immediate
           constexpr uint32_t kAHi = (uint32_t)(kRowBytes >> 4) | (1u << 14);
           constexpr uint32_t kBHi = (uint32_t)(128 >> 4) | (1u << 14);
+          const uint32_t tacc = tmem_base + (buf * 2 + g) * 128;
+          if (g == 1) release_plane(d0 - 1);  // never read by this issuer
 #pragma unroll 1
           for (int kd = 0; kd < 3; ++kd) {
-            if (kd == 0) {
-              wait_plane(d0 - 1);
-              wait_plane(d0);
-            } else {
-              wait_plane(d0 + kd);
-            }
-            uint32_t a_lo[2];
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const uint32_t slot = plane_seq(d0 + g + kd - 1) % kPlaneSlots;
-              a_lo[g] = ((sbase + kSmemPlanes + slot * kPlaneBytes) >> 4) | ((uint32_t)(kChunkBytes >> 4) << 16);
-            }
+            const int dplane = d0 + g + kd - 1;  // input plane of this issuer's output plane for this kd
+            wait_plane(dplane);
+            const uint32_t slot = plane_seq(dplane) % kPlaneSlots;
+            const uint32_t a_lo = ((sbase + kSmemPlanes + slot * kPlaneBytes) >> 4) | ((uint32_t)(kChunkBytes >> 4) << 16);
 #pragma unroll
             for (int khw = 0; khw < 9; ++khw) {
               const int kh = khw / 3, kw = khw % 3;
@@ -277,23 +275,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_k3_c96_kernel(const __grid
               tc_fence_after();
               const uint32_t b_lo = ((sbase + kSmemWeights + st * kTapBytes) >> 4) | ((uint32_t)((kC * 16) >> 4) << 16);
 #pragma unroll
-              for (int g = 0; g < 2; ++g) {
-                const uint32_t tacc = tmem_base + (buf * 2 + g) * 128;
-#pragma unroll
-                for (int ks = 0; ks < kKSteps; ++ks) {
-                  const uint32_t al = a_lo[g] + (uint32_t)((kh * kRowBytes + kw * 16 + 2 * ks * kChunkBytes) >> 4);
-                  const uint32_t bl = b_lo + (uint32_t)((2 * ks * kC * 16) >> 4);
-                  const uint64_t ad = ((uint64_t)kAHi << 32) | al;
-                  const uint64_t bd = ((uint64_t)kBHi << 32) | bl;
-                  tc_mma(tacc, ad, bd, kIdesc, (kd | khw | ks) != 0);
-                }
+              for (int ks = 0; ks < kKSteps; ++ks) {
+                const uint32_t al = a_lo + (uint32_t)((kh * kRowBytes + kw * 16 + 2 * ks * kChunkBytes) >> 4);
+                const uint32_t bl = b_lo + (uint32_t)((2 * ks * kC * 16) >> 4);
+                const uint64_t ad = ((uint64_t)kAHi << 32) | al;
+                const uint64_t bd = ((uint64_t)kBHi << 32) | bl;
+                tc_mma(tacc, ad, bd, kIdesc, (kd | khw | ks) != 0);
               }
               tc_commit(bar(BAR_WEMPTY + st));
             }
-            if (kd == 0) {
-              release_plane(d0 - 1);
-              release_plane(d0);
-            }
+            // input planes d0-1 and d0 are not needed by later groups: g = 0 read them at kd = 0 / 1, g = 1 read d0 at
+            // kd = 0. Planes d0+1 and d0+2 stay for the next group unless this is the item's last group.
+            if (g == 0 && kd <= 1) release_plane(d0 - 1 + kd);
+            if (g == 1 && kd == 0) release_plane(d0);
           }
           if (d0 + 2 >= it.d_end) {
             release_plane(d0 + 1);
