@@ -149,24 +149,39 @@ class PharmacoNet:
     # ------------------------------------------------------------------ shared front part
     @torch.no_grad()
     def _features_and_hotspots(self, protein_data, nchw: bool = True):
-        image, mask, token_pos, tokens = protein_data
+        return self._features_and_hotspots_batch([protein_data], nchw)[0]
+
+    @torch.no_grad()
+    def _features_and_hotspots_batch(self, protein_data_list, nchw: bool = True):
+        """module.py:141-170 / 216-258 for several pockets at once: one batched forward_feature, token head and
+        cavity head, then the per-pocket token filter."""
         dev = self.device
-        image = image.to(dev, torch.float32)
-        token_pos = token_pos.to(dev, torch.float32)
-        tokens = tokens.to(dev, torch.long)
-        mask = mask.to(dev, torch.bool)
-        feats = self.model.forward_feature(image.unsqueeze(0), nchw=nchw)
-        scores, tfeat = self.model.forward_token_prediction(feats[-1], [tokens])
-        abs_scores = scores[0].sigmoid()
-        narrow, wide = self.model.forward_cavity_extraction(feats[-1])
-        narrow = narrow[0].sigmoid() > self.focus_threshold  # [1, D, H, W]
-        wide = wide[0].sigmoid() > self.focus_threshold
-        keep, rel = self.select_hotspots(tokens, abs_scores, narrow, wide)
-        idx = torch.nonzero(keep).reshape(-1)
-        return dict(
-            feats=feats, mask=mask, narrow=narrow, wide=wide, hotspots=tokens[idx], positions=token_pos[idx],
-            features=tfeat[0][idx], rel_scores=rel[idx].cpu().tolist(),
-        )  # fmt: skip
+        images = torch.stack([pd[0].to(dev, torch.float32) for pd in protein_data_list])
+        masks = [pd[1].to(dev, torch.bool) for pd in protein_data_list]
+        token_pos = [pd[2].to(dev, torch.float32) for pd in protein_data_list]
+        tokens = [pd[3].to(dev, torch.long) for pd in protein_data_list]
+        feats = self.model.forward_feature(images, nchw=nchw)
+        scores, tfeat = self.model.forward_token_prediction(feats[-1], tokens)
+        narrow_all, wide_all = self.model.forward_cavity_extraction(feats[-1])
+        out = []
+        for b in range(len(protein_data_list)):
+            abs_scores = scores[b].sigmoid()
+            narrow = narrow_all[b].sigmoid() > self.focus_threshold  # [1, D, H, W]
+            wide = wide_all[b].sigmoid() > self.focus_threshold
+            keep, rel = self.select_hotspots(tokens[b], abs_scores, narrow, wide)
+            idx = torch.nonzero(keep).reshape(-1)
+            fb = cnn.Features(f[b : b + 1] for f in feats)
+            for src, dst in zip(feats, fb):
+                twin = getattr(src, "_pm_c8", None)
+                if twin is not None:
+                    dst._pm_c8 = twin[b : b + 1]
+            out.append(
+                dict(
+                    feats=fb, mask=masks[b], narrow=narrow, wide=wide, hotspots=tokens[b][idx], positions=token_pos[b][idx],
+                    features=tfeat[b][idx], rel_scores=rel[idx].cpu().tolist(),
+                )
+            )  # fmt: skip
+        return out
 
     def select_hotspots(self, tokens, abs_scores, cavity_narrow, cavity_wide):
         """module.py:235-253 for all tokens at once. relative score = fraction of the type's training-score
@@ -213,8 +228,29 @@ class PharmacoNet:
     # ------------------------------------------------------------------ module.py:215-309
     @torch.no_grad()
     def create_density_maps(self, protein_data) -> list[HotspotInfo]:
+        return self.create_density_maps_batch([protein_data])[0]
+
+    @torch.no_grad()
+    def create_models(self, protein_data_list, centers=None, pdbblocks=None, chunk: int = 8) -> list[PharmacophoreModel]:
+        """Several pockets -> several PharmacophoreModels (BASELINE configs[4] shape): the CNN runs on chunks of
+        `chunk` pockets, the graph construction per pocket on the host."""
+        n = len(protein_data_list)
+        centers = centers or [(0.0, 0.0, 0.0)] * n
+        pdbblocks = pdbblocks or [""] * n
+        models = []
+        for lo in range(0, n, chunk):
+            infos = self.create_density_maps_batch(protein_data_list[lo : lo + chunk])
+            for k, info in enumerate(infos):
+                models.append(PharmacophoreModel.create(pdbblocks[lo + k], tuple(float(c) for c in centers[lo + k]), info))
+        return models
+
+    @torch.no_grad()
+    def create_density_maps_batch(self, protein_data_list) -> list[list[HotspotInfo]]:
         self.print_log("debug", f"Protein-based Pharmacophore Modeling... (device: {self.device})")
-        r = self._features_and_hotspots(protein_data, nchw=False)  # the maps stay in the kernels' layout
+        # the maps stay in the kernels' layout
+        return [self._density_maps_of(r) for r in self._features_and_hotspots_batch(protein_data_list, nchw=False)]
+
+    def _density_maps_of(self, r) -> list[HotspotInfo]:
         hotspots, feats = r["hotspots"], r["feats"]
         logits = []
         if hotspots.shape[0] > 0:

@@ -186,3 +186,30 @@ def test_fused_swin_ops_match_op_by_op_path(setup):
             assert rel <= 3e-2, rel  # bf16 GEMM operands through 12 blocks
     finally:
         bb.fused, bb.precision = True, "fp32"
+
+
+def test_batched_pockets_match_single_pocket_calls():
+    from pharmaconet_b200.module import PharmacoNet
+
+    gold = np.load(os.path.join(GOLDEN, "cnn_pipeline_golden.npz"))
+    man = json.load(open(os.path.join(GOLDEN, "cnn_manifest.json")))
+    buf = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, "cnn_buffers.npz")).items()}
+    net = PharmacoNet("cuda:0", verbose=False, checkpoint=cnn_weights.synth_checkpoint(man, buf, 0))
+    tokens = torch.from_numpy(gold["tokens"]).long()
+    token_pos = (tokens[:, :3].float() - 31.5) * 0.5
+    data = []
+    for seed in (0, 5):
+        g = torch.Generator().manual_seed(seed)
+        image = torch.rand((33, 64, 64, 64), generator=g)
+        mask = torch.rand((64, 64, 64), generator=torch.Generator().manual_seed(seed + 2)) < 0.8
+        data.append((image, mask, token_pos, tokens))
+    batched = net.create_density_maps_batch(data)
+    for pd, infos_b in zip(data, batched):
+        infos_s = net.create_density_maps(pd)
+        assert abs(len(infos_s) - len(infos_b)) <= 1
+        if len(infos_s) == len(infos_b):
+            nz_s = np.array([int((i["point_map"] > 0).sum()) for i in infos_s])
+            nz_b = np.array([int((i["point_map"] > 0).sum()) for i in infos_b])
+            assert np.abs(nz_s - nz_b).max() <= 0.02 * max(1, nz_s.max())
+    models = net.create_models(data, centers=[(0.0, 0.0, 0.0), (1.0, 2.0, 3.0)])
+    assert len(models) == 2 and all(len(m.nodes) > 0 for m in models)
