@@ -53,7 +53,7 @@ struct WarpLayout {
   int rows;         // pair-score rows (128 B each)
   int dn_cap;       // max ligand nodes in the selected levels (distance table is dn_cap x dn_cap rows)
   int rec_cap;      // max node-match records
-  size_t off_rows, off_dist, off_v, off_prow, off_masks, off_rowbase, off_srow, off_nmoff, off_geo, off_rec,
+  size_t off_rows, off_dist, off_v, off_prow, off_masks, off_tot, off_rowbase, off_srow, off_nmoff, off_geo, off_rec,
       off_entmc, off_entlev, off_nmcnt, off_lnode, off_mlist;
   size_t mlist_cap;
   size_t bytes;     // per warp, multiple of 256
@@ -76,6 +76,7 @@ __host__ __device__ inline WarpLayout make_layout(int n_model_clusters, int scra
   L.off_v = o;       o += (size_t)L.pair_cap * 4 * W;
   L.off_prow = o;    o += (size_t)L.pair_cap * 4;
   L.off_masks = o;   o += (size_t)kSlots * L.t_cap * 4 * W;
+  L.off_tot = o;     o += (size_t)kSlots * 128 * W;
   L.off_rowbase = o; o += (size_t)L.t_cap * 4;
   L.off_srow = o;    o += (size_t)L.t_cap * 4;
   L.off_nmoff = o;   o += (size_t)L.t_cap * 4;
@@ -117,13 +118,21 @@ __host__ __device__ inline size_t smem_model_bytes(int nm, int km, int n_cluster
   return align_up(o, 16);
 }
 
+// Per-warp shared memory of the DFS: the per-depth conformer totals and the candidate-mask stack of the common case
+// (the mask stack is triangular: depth s only keeps the entries of levels >= s). Ligands that need more depth or more
+// mask words use the same layout in the global workspace instead.
+constexpr int kSmemTotFloats = 12 * 32;  // 12 depths of 32 conformers (6 of 64, 3 of 128)
+constexpr int kSmemMaskWords = 256;
 template <int W>
 struct WarpSmem {
-  float tot[kSlots][W * 32];  // per-depth conformer totals
+  float tot[kSmemTotFloats];
+  uint32_t mk[kSmemMaskWords];
   int lev_start[kMaxDepth + 1];
   int lev_q[kMaxDepth];       // ligand cluster (global CSR index) of each level
   int lev_nbase[kMaxDepth];   // first local node id of each level
-  int pad[3];
+  int lev_run[kMaxDepth];     // pair-table index of the level's first entry against the first later entry
+  int moff[kMaxDepth];        // mask stack: word offset of depth s, minus lev_start[s] (index with the entry number)
+  int pad[2];
 };
 
 struct KernelArgs {
@@ -203,6 +212,27 @@ __device__ __forceinline__ void pair_term(const SmemModel& sm, const uint8_t* __
     npass[w] = 0;
     lik[w] = 0.0f;
   }
+  if (M <= 2 && N <= 2) {
+    // by far the most common multi-node case (small model clusters): straight-line code, same evaluation order
+    const float4* row0 = sm.edge + (r1.y & 255u) * sm.nm;
+    const unsigned b0 = r2.y & 255u, b1 = (r2.y >> 8) & 255u;
+    eval_edge<W>(row0[b0], d, lik, npass);
+    if (N == 2) eval_edge<W>(row0[b1], d, lik, npass);
+    if (M == 2) {
+      const float4* row1 = sm.edge + ((r1.y >> 8) & 255u) * sm.nm;
+      eval_edge<W>(row1[b0], d, lik, npass);
+      if (N == 2) eval_edge<W>(row1[b1], d, lik, npass);
+    }
+    const int mn = M * N;  // 2 or 4
+    const float inv = mn == 2 ? 0.5f : 0.25f;
+    const int half = mn >> 1;  // (mn + 1) / 2
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      nfail[w] += (npass[w] < half) ? 1 : 0;
+      sc[w] += lik[w] * inv;
+    }
+    return;
+  }
   if (M <= 4 && N <= 4) {
     // the common multi-node case, fully unrolled: model nodes come out of the record words with constant shifts and
     // the (warp-uniform) bounds only skip blocks
@@ -233,7 +263,7 @@ __device__ __forceinline__ void pair_term(const SmemModel& sm, const uint8_t* __
 }
 
 #ifndef PM_BLOCK_THREADS
-#define PM_BLOCK_THREADS 256
+#define PM_BLOCK_THREADS 384
 #endif
 #ifndef PM_MIN_BLOCKS
 #define PM_MIN_BLOCKS 2
@@ -343,6 +373,7 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
 
       // ================= phase 0: levels, entries, node-match records (graph_match.py:85-92, 124-172)
       int L = 0, T = 0, NL = 0;
+      int mask_need = 0;  // entries of the triangular mask stack
       bool overflow = false;
       for (int q = q0; q < q1 && L < kMaxDepth && !overflow; ++q) {
         const int c0 = B.cluster_node_off[q], c1 = B.cluster_node_off[q + 1];
@@ -488,6 +519,11 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
             const int s = ws.lev_start[l], e_end = ws.lev_start[l + 1];
             const int width = T - e_end;
             for (int e = s + lane; e < e_end; e += 32) rowbase[e] = run + (e - s) * width - e_end;
+            if (lane == 0) {
+              ws.lev_run[l] = run;
+              ws.moff[l] = mask_need - s;
+            }
+            mask_need += T - s;
             run += (e_end - s) * width;
           }
           st_pairs = (uint32_t)run;
@@ -527,6 +563,9 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
         status = PMNET_LIG_EMPTY;
       } else {
         // ================= phase 1: self scores and pair table (graph_match.py:222-279)
+        // (row / distance indices fit 32 bits: at most 2^17 rows and 255^2 node pairs of 128 conformer slots)
+        const float* const dist_l = dist + lane;
+        float* const rows_l = rows + lane;
         int nrows = 0;
         for (int e = 0; e < T && !overflow; ++e) {
           const int cnt = nmcnt[e];
@@ -542,12 +581,12 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
             const uint32_t off = nmoff[e];
             for (int i = 0; i < cnt - 1; ++i) {
               const uint2 r1 = rec[off + i];
-              const float* drow = dist + ((size_t)rec_node(r1) * NL) * CW + lane;
+              const int drow = rec_node(r1) * NL;
               for (int j = i + 1; j < cnt; ++j) {
                 const uint2 r2 = rec[off + j];
                 float d[W];
 #pragma unroll
-                for (int w = 0; w < W; ++w) d[w] = drow[(size_t)rec_node(r2) * CW + 32 * w];
+                for (int w = 0; w < W; ++w) d[w] = dist_l[(drow + rec_node(r2)) * CW + 32 * w];
                 pair_term<W>(sm, mlist, d, r1, r2, sc, nf);
               }
             }
@@ -557,7 +596,7 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
             }
             r = nrows++;
 #pragma unroll
-            for (int w = 0; w < W; ++w) rows[((size_t)r * W + w) * 32 + lane] = sc[w];
+            for (int w = 0; w < W; ++w) rows_l[(r * W + w) * 32] = sc[w];
           }
           if (lane == 0) srow[e] = r;
         }
@@ -613,12 +652,12 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
                   bool dead = false;
                   for (int a = 0; a < cnt1; ++a) {
                     const uint2 r1 = rec[off1 + a];
-                    const float* drow = dist + ((size_t)rec_node(r1) * NL) * CW + lane;
+                    const int drow = rec_node(r1) * NL;
                     for (int b = 0; b < cnt2; ++b) {
                       const uint2 r2 = rec[off2 + b];
                       float d[W];
 #pragma unroll
-                      for (int w = 0; w < W; ++w) d[w] = drow[(size_t)rec_node(r2) * CW + 32 * w];
+                      for (int w = 0; w < W; ++w) d[w] = dist_l[(drow + rec_node(r2)) * CW + 32 * w];
                       pair_term<W>(sm, mlist, d, r1, r2, sc, nfail);
                     }
                     // every conformer already failed: the pair is invalid whatever follows
@@ -645,7 +684,7 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
                     }
                     r = nrows++;
 #pragma unroll
-                    for (int w = 0; w < W; ++w) rows[((size_t)r * W + w) * 32 + lane] = sc[w];
+                    for (int w = 0; w < W; ++w) rows_l[(r * W + w) * 32] = sc[w];
                   }
                 }
                 if (lane == 0) {
@@ -667,11 +706,14 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
           int st_cursor = 0, st_maxm = 0, st_nchild = 0, st_phase = 0, st_nmatch = 0, st_entry = -1, st_mslot = 0,
               st_tslot = 0, st_pbase = 0;
           unsigned st_alive[W];
+          // stacks in shared memory when they fit (the common case), else in the workspace; same layout
+          uint32_t* const mk = (mask_need * W <= kSmemMaskWords) ? ws.mk : masks;
+          float* const tot_l = ((L * CW <= kSmemTotFloats) ? ws.tot : (float*)(wbase + LY.off_tot)) + lane;
 #pragma unroll
           for (int w = 0; w < W; ++w) {
             st_alive[w] = 0;
-            for (int e = lane; e < T; e += 32) masks[(size_t)e * W + w] = cfull[w];
-            ws.tot[0][32 * w + lane] = 0.0f;
+            for (int e = lane; e < T; e += 32) mk[e * W + w] = cfull[w];  // depth 0: moff[0] = 0
+            tot_l[32 * w] = 0.0f;
           }
           if (lane == 0) {
             st_cursor = 0;  // lev_start[0]
@@ -687,9 +729,88 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
             const int phase = __shfl_sync(kFull, st_phase, d);
             const int mslot = __shfl_sync(kFull, st_mslot, d);
             const int tslot = __shfl_sync(kFull, st_tslot, d);
-            const uint32_t* pm = masks + (size_t)mslot * LY.t_cap * W;
+            const uint32_t* pm = mk + ws.moff[mslot] * W;
+            // lanes 1..d that hold a matched ancestor (or this node itself). A candidate's mask is the AND of the
+            // validity words of its pairs with every matched ancestor, so each of those pairs has a score row.
+            const bool is_anc = lane >= 1 && lane <= d && st_entry >= 0;
             bool do_return = false;
-            if (phase == 0) {
+            if (phase == 0 && y == L - 1) {
+              // ---- every child of this node is a leaf (graph_match.py:103-109): take them all in one pass
+              const int end = T;
+              float tt[W];
+#pragma unroll
+              for (int w = 0; w < W; ++w) tt[w] = tot_l[tslot * CW + 32 * w];
+              int nleaf = 0;
+              for (int cur = ws.lev_start[y]; cur < end; cur += 32) {
+                const int idx = cur + lane;
+                unsigned mw[W];
+                unsigned anyw = 0;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                  mw[w] = (idx < end) ? pm[idx * W + w] : 0u;
+                  anyw |= mw[w];
+                }
+                unsigned bal = __ballot_sync(kFull, anyw != 0u);
+                if (bal == 0u) continue;
+                // row indices of the next candidate are fetched while the current one is summed
+                int nf = cur + __ffs(bal) - 1;
+                int myrow_n = is_anc ? prow[st_pbase + nf] : -1;
+                int sr_n = srow[nf];
+                while (bal) {
+                  const int src = __ffs(bal) - 1;
+                  bal &= bal - 1;
+                  const int myrow = myrow_n, sr = sr_n;
+                  if (bal) {
+                    nf = cur + __ffs(bal) - 1;
+                    myrow_n = is_anc ? prow[st_pbase + nf] : -1;
+                    sr_n = srow[nf];
+                  }
+                  float t[W], self[W];
+#pragma unroll
+                  for (int w = 0; w < W; ++w) {
+                    self[w] = (sr >= 0) ? rows_l[(sr * W + w) * 32] : 0.0f;
+                    t[w] = 0.0f;
+                  }
+                  // lanes 1..d hold the pair-row index of their depth (-1: unmatched); four loads in flight per round
+                  for (int d0 = 1; d0 <= d; d0 += 4) {
+                    int rr[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) rr[u] = __shfl_sync(kFull, myrow, d0 + u);
+                    float vv[4][W];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                      for (int w = 0; w < W; ++w)
+                        vv[u][w] = (rr[u] >= 0) ? rows_l[(rr[u] * W + w) * 32] : 0.0f;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                      for (int w = 0; w < W; ++w) t[w] += vv[u][w];
+                  }
+#pragma unroll
+                  for (int w = 0; w < W; ++w) {
+                    const unsigned al = __shfl_sync(kFull, mw[w], src);
+                    if ((al >> lane) & 1u) best[w] = fmaxf(best[w], (tt[w] + self[w]) + t[w]);
+                  }
+                  ++nleaf;
+                }
+              }
+              st_nodes += nleaf;
+              st_leaves += nleaf;
+              const int nmatch = __shfl_sync(kFull, st_nmatch, d);
+              if (lane == d) st_maxm = nleaf > 0 ? 1 : 0;
+              if (nleaf == 0 || nmatch + 1 < PMNET_MIN_MATCHES) {
+                // the None leaf (tree.py:98)
+                ++st_nodes;
+                ++st_leaves;
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                  const unsigned al = __shfl_sync(kFull, st_alive[w], d);
+                  if ((al >> lane) & 1u) best[w] = fmaxf(best[w], tt[w]);
+                }
+              }
+              do_return = true;
+            } else if (phase == 0) {
               int cur = __shfl_sync(kFull, st_cursor, d);
               const int end = ws.lev_start[y + 1];
               int found = -1;
@@ -702,7 +823,7 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
                 unsigned anyw = 0;
 #pragma unroll
                 for (int w = 0; w < W; ++w) {
-                  mw[w] = (idx < end) ? pm[(size_t)idx * W + w] : 0u;
+                  mw[w] = (idx < end) ? pm[idx * W + w] : 0u;
                   anyw |= mw[w];
                 }
                 const unsigned bal = __ballot_sync(kFull, anyw != 0u);
@@ -716,84 +837,78 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
                 cur += 32;
               }
               if (found >= 0) {
-                // ---- matched child (y, found): ClusterMatchTree.__init__ (tree.py:33-41)
+                // ---- matched child (y, found): ClusterMatchTree.__init__ (tree.py:33-41); it is not a leaf
                 ++st_nodes;
                 if (lane == d) {
                   st_cursor = found + 1;
                   st_nchild += 1;
                 }
-                // pair rows with the matched ancestors: lane dd looks up its own ancestor's row, then the rows
-                // are added in top-down order like the reference's running sums (tree.py:78-82)
-                const int myrow = (lane >= 1 && lane <= d && st_entry >= 0) ? prow[st_pbase + found] : -1;
-                unsigned anc = __ballot_sync(kFull, myrow >= 0);
+                // everything that depends only on `found` is requested first: the ancestors' pair-row indices,
+                // the self row index, the parent's totals and the first chunk of the child's masks
+                const int myrow = is_anc ? prow[st_pbase + found] : -1;
+                const int sr = srow[found];
+                const int pbc = ws.lev_run[y] + (found - ws.lev_start[y]) * (T - end) - end;
+                uint32_t* nm_ = mk + ws.moff[d + 1] * W;
+                const int e2a = end + lane;
+                unsigned pmv[W], vtv[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                  pmv[w] = (e2a < T) ? pm[e2a * W + w] : 0u;
+                  vtv[w] = (e2a < T) ? Vt[(pbc + e2a) * W + w] : 0u;
+                }
+                float t[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                  t[w] = tot_l[tslot * CW + 32 * w];
+                  if (sr >= 0) t[w] += rows_l[(sr * W + w) * 32];
+                }
+                // pair rows with the matched ancestors (tree.py:78-82), four independent row loads per round
                 float acc[W];
 #pragma unroll
                 for (int w = 0; w < W; ++w) acc[w] = 0.0f;
-                while (anc) {
-                  // four independent row loads in flight per round; the adds stay in top-down order
+                for (int d0 = 1; d0 <= d; d0 += 4) {
                   int rr[4];
 #pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    const int dd = anc ? (__ffs(anc) - 1) : 0;
-                    const int r = __shfl_sync(kFull, myrow, dd);
-                    rr[u] = anc ? r : -1;
-                    anc &= anc - 1;
-                  }
+                  for (int u = 0; u < 4; ++u) rr[u] = __shfl_sync(kFull, myrow, d0 + u);
                   float vv[4][W];
 #pragma unroll
                   for (int u = 0; u < 4; ++u)
 #pragma unroll
                     for (int w = 0; w < W; ++w)
-                      vv[u][w] = (rr[u] >= 0) ? rows[((size_t)rr[u] * W + w) * 32 + lane] : 0.0f;
+                      vv[u][w] = (rr[u] >= 0) ? rows_l[(rr[u] * W + w) * 32] : 0.0f;
 #pragma unroll
                   for (int u = 0; u < 4; ++u)
-                    if (rr[u] >= 0) {
 #pragma unroll
-                      for (int w = 0; w < W; ++w) acc[w] += vv[u][w];
-                    }
+                    for (int w = 0; w < W; ++w) acc[w] += vv[u][w];
                 }
-                float t[W];
-                const int sr = srow[found];
+                const int nmatch = __shfl_sync(kFull, st_nmatch, d) + 1;
+                // the child's candidate masks: parent mask & conformers alive in the child & pair validity
+                if (e2a < T) {
 #pragma unroll
-                for (int w = 0; w < W; ++w) {
-                  t[w] = ws.tot[tslot][32 * w + lane];
-                  if (sr >= 0) t[w] += rows[((size_t)sr * W + w) * 32 + lane];
-                  t[w] += acc[w];
+                  for (int w = 0; w < W; ++w) nm_[e2a * W + w] = pmv[w] & alive2[w] & vtv[w];
                 }
-                if (y == L - 1) {
-                  // leaf (graph_match.py:103-109)
-                  ++st_leaves;
+                for (int e2 = e2a + 32; e2 < T; e2 += 32) {
 #pragma unroll
                   for (int w = 0; w < W; ++w)
-                    if ((alive2[w] >> lane) & 1u) best[w] = fmaxf(best[w], t[w]);
-                  if (lane == d) st_maxm = max(st_maxm, 1);
-                } else {
-                  const int nmatch = __shfl_sync(kFull, st_nmatch, d) + 1;
-                  const int pbc = rowbase[found];
-                  uint32_t* nm_ = masks + (size_t)(d + 1) * LY.t_cap * W;
-                  for (int e2 = ws.lev_start[y + 1] + lane; e2 < T; e2 += 32) {
-#pragma unroll
-                    for (int w = 0; w < W; ++w)
-                      nm_[(size_t)e2 * W + w] = pm[(size_t)e2 * W + w] & alive2[w] & Vt[(size_t)(pbc + e2) * W + w];
-                  }
-#pragma unroll
-                  for (int w = 0; w < W; ++w) ws.tot[d + 1][32 * w + lane] = t[w];
-                  if (lane == d + 1) {
-                    st_cursor = ws.lev_start[y + 1];
-                    st_maxm = 0;
-                    st_nchild = 0;
-                    st_phase = 0;
-                    st_nmatch = nmatch;
-                    st_entry = found;
-                    st_mslot = d + 1;
-                    st_tslot = d + 1;
-                    st_pbase = pbc;
-#pragma unroll
-                    for (int w = 0; w < W; ++w) st_alive[w] = alive2[w];
-                  }
-                  __syncwarp();
-                  d = d + 1;
+                    nm_[e2 * W + w] = pm[e2 * W + w] & alive2[w] & Vt[(pbc + e2) * W + w];
                 }
+#pragma unroll
+                for (int w = 0; w < W; ++w) tot_l[(d + 1) * CW + 32 * w] = t[w] + acc[w];
+                if (lane == d + 1) {
+                  st_cursor = end;
+                  st_maxm = 0;
+                  st_nchild = 0;
+                  st_phase = 0;
+                  st_nmatch = nmatch;
+                  st_entry = found;
+                  st_mslot = d + 1;
+                  st_tslot = d + 1;
+                  st_pbase = pbc;
+#pragma unroll
+                  for (int w = 0; w < W; ++w) st_alive[w] = alive2[w];
+                }
+                __syncwarp();
+                d = d + 1;
                 continue;
               }
               // ---- no matched child left: None child iff nothing matched or too few matches so far (tree.py:98)
@@ -801,39 +916,29 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
               const int nmatch = __shfl_sync(kFull, st_nmatch, d);
               const int maxm = __shfl_sync(kFull, st_maxm, d);
               if (nchild == 0 || nmatch + maxm < PMNET_MIN_MATCHES) {
+                // the None child is not a leaf here (y < L - 1): same masks and totals, one level down
                 ++st_nodes;
                 if (lane == d) st_phase = 1;
                 unsigned alive[W];
 #pragma unroll
                 for (int w = 0; w < W; ++w) alive[w] = __shfl_sync(kFull, st_alive[w], d);
-                if (y == L - 1) {
-                  ++st_leaves;
+                if (lane == d + 1) {
+                  st_cursor = end;
+                  st_maxm = 0;
+                  st_nchild = 0;
+                  st_phase = 0;
+                  st_nmatch = nmatch;
+                  st_entry = -1;
+                  st_mslot = mslot;
+                  st_tslot = tslot;
+                  st_pbase = 0;
 #pragma unroll
-                  for (int w = 0; w < W; ++w) {
-                    const float t = ws.tot[tslot][32 * w + lane];
-                    if ((alive[w] >> lane) & 1u) best[w] = fmaxf(best[w], t);
-                  }
-                  do_return = true;
-                } else {
-                  if (lane == d + 1) {
-                    st_cursor = ws.lev_start[y + 1];
-                    st_maxm = 0;
-                    st_nchild = 0;
-                    st_phase = 0;
-                    st_nmatch = nmatch;
-                    st_entry = -1;
-                    st_mslot = mslot;
-                    st_tslot = tslot;
-                    st_pbase = 0;
-#pragma unroll
-                    for (int w = 0; w < W; ++w) st_alive[w] = alive[w];
-                  }
-                  d = d + 1;
-                  continue;
+                  for (int w = 0; w < W; ++w) st_alive[w] = alive[w];
                 }
-              } else {
-                do_return = true;
+                d = d + 1;
+                continue;
               }
+              do_return = true;
             } else {
               do_return = true;  // the None child returned
             }
