@@ -147,6 +147,7 @@ struct KernelArgs {
   int scratch_rows;
   int n_cluster_nodes;
   int conf_stride;  // floats per ligand in out_conf (32 * W)
+  WarpLayout ly;    // computed once on the host: the kernel reads the offsets from the constant bank
 };
 
 __device__ __forceinline__ float ld_coord(const float* xyz, int stride, int node, int axis, int lane, bool on) {
@@ -233,24 +234,12 @@ __device__ __forceinline__ void pair_term(const SmemModel& sm, const uint8_t* __
     }
     return;
   }
-  if (M <= 4 && N <= 4) {
-    // the common multi-node case, fully unrolled: model nodes come out of the record words with constant shifts and
-    // the (warp-uniform) bounds only skip blocks
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      if (a < M) {
-        const float4* row = sm.edge + ((r1.y >> (8 * a)) & 255u) * sm.nm;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          if (b < N) eval_edge<W>(row[(r2.y >> (8 * b)) & 255u], d, lik, npass);
-        }
-      }
-    }
-  } else {
-    for (int a = 0; a < M; ++a) {
-      const float4* row = sm.edge + rec_model_node(r1, a, mlist) * sm.nm;
-      for (int b = 0; b < N; ++b) eval_edge<W>(row[rec_model_node(r2, b, mlist)], d, lik, npass);
-    }
+  // larger matches (wide model clusters): plain loops, model nodes from the record word or the spill list
+#pragma unroll 1
+  for (int a = 0; a < M; ++a) {
+    const float4* row = sm.edge + rec_model_node(r1, a, mlist) * sm.nm;
+#pragma unroll 1
+    for (int b = 0; b < N; ++b) eval_edge<W>(row[rec_model_node(r2, b, mlist)], d, lik, npass);
   }
   const int mn = M * N;
   float inv;
@@ -263,7 +252,7 @@ __device__ __forceinline__ void pair_term(const SmemModel& sm, const uint8_t* __
 }
 
 #ifndef PM_BLOCK_THREADS
-#define PM_BLOCK_THREADS 384
+#define PM_BLOCK_THREADS 512
 #endif
 #ifndef PM_MIN_BLOCKS
 #define PM_MIN_BLOCKS 2
@@ -316,9 +305,13 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
   __syncthreads();
 
   // ---- per-warp scratch
-  const WarpLayout LY = make_layout(KM, args.scratch_rows, W);
+  const WarpLayout& LY = args.ly;
   const int gwarp = blockIdx.x * warps_per_block + warp_in_block;
   unsigned char* wbase = args.workspace + kHeaderBytes + (size_t)gwarp * LY.bytes;
+  // opaque to the optimiser: keeps the warp's base in registers instead of re-deriving it from the thread and
+  // block ids inside the inner loops when registers are tight
+  asm volatile("" : "+l"(wbase));
+  __builtin_assume(__isGlobal(wbase));
   float* const rows = (float*)(wbase + LY.off_rows);
   uint32_t* const Vt = (uint32_t*)(wbase + LY.off_v);
   int32_t* const prow = (int32_t*)(wbase + LY.off_prow);
@@ -1063,6 +1056,7 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
   a.out_stats = out_stats;
   a.workspace = (unsigned char*)workspace;
   a.scratch_rows = c.scratch_rows;
+  a.ly = make_layout(model->n_clusters, c.scratch_rows, conf_words(c.max_conformers));
   const int32_t n_cluster_nodes = model->n_cluster_nodes;
   if (n_cluster_nodes < 0 || n_cluster_nodes > 65535) {
     set_err("pmnet_score_batch: n_cluster_nodes out of range");
