@@ -170,10 +170,10 @@ __device__ __forceinline__ float gauss(float s2) {
 }
 
 // Node-match record, 8 bytes (one per ligand node of an entry with >= 1 matched model node, graph_match.py:139-172):
-//   .x bits 0-7 local ligand node id, 8-15 M = number of matched model nodes, 16-31 offset of the model-node bytes
+//   .x bits 0-7 local ligand node id, 8-15 M - 1 (M = number of matched model nodes), 16-31 offset of the model-node bytes
 //      in `mlist` when M > 4;  .y = the first four matched model nodes, one byte each (all of them when M <= 4).
 __device__ __forceinline__ int rec_node(uint2 r) { return r.x & 255u; }
-__device__ __forceinline__ int rec_m(uint2 r) { return (r.x >> 8) & 255u; }
+__device__ __forceinline__ int rec_m(uint2 r) { return (int)((r.x >> 8) & 255u) + 1; }
 __device__ __forceinline__ int rec_model_node(uint2 r, int a, const uint8_t* __restrict__ mlist) {
   return (a < 4) ? (int)((r.y >> (8 * a)) & 255u) : (int)mlist[(r.x >> 16) + a];
 }
@@ -194,8 +194,7 @@ __device__ __forceinline__ void eval_edge(const float4 e, const float (&d)[W], f
 template <int W>
 __device__ __forceinline__ void pair_term(const SmemModel& sm, const uint8_t* __restrict__ mlist, const float (&d)[W],
                                           uint2 r1, uint2 r2, float (&sc)[W], int (&nfail)[W]) {
-  const int M = rec_m(r1), N = rec_m(r2);
-  if (M == 1 && N == 1) {
+  if (((r1.x | r2.x) & 0xff00u) == 0u) {  // M == 1 and N == 1
     const float4 e = sm.edge[(r1.y & 255u) * sm.nm + (r2.y & 255u)];
 #pragma unroll
     for (int w = 0; w < W; ++w) {
@@ -206,6 +205,7 @@ __device__ __forceinline__ void pair_term(const SmemModel& sm, const uint8_t* __
     }
     return;
   }
+  const int M = rec_m(r1), N = rec_m(r2);
   int npass[W];
   float lik[W];
 #pragma unroll
@@ -213,7 +213,7 @@ __device__ __forceinline__ void pair_term(const SmemModel& sm, const uint8_t* __
     npass[w] = 0;
     lik[w] = 0.0f;
   }
-  if (M <= 2 && N <= 2) {
+  if (((r1.x | r2.x) & 0xfe00u) == 0u) {  // M <= 2 and N <= 2
     // by far the most common multi-node case (small model clusters): straight-line code, same evaluation order
     const float4* row0 = sm.edge + (r1.y & 255u) * sm.nm;
     const unsigned b0 = r2.y & 255u, b1 = (r2.y >> 8) & 255u;
@@ -251,14 +251,21 @@ __device__ __forceinline__ void pair_term(const SmemModel& sm, const uint8_t* __
   }
 }
 
+// Launch shape. Up to 32 conformers (W = 1): one CTA of 32 warps per SM at 64 registers per thread - the kernel is
+// bound by instruction issue and by the latency of its scratch reads, and 32 resident warps hide that best
+// (measured: 28 / 38 / 47 / 52.8 M conformers/s at 16 / 16 / 24 / 32 warps per SM across the round-1 versions).
+// More conformers per lane need more registers: two CTAs of 8 warps.
 #ifndef PM_BLOCK_THREADS
-#define PM_BLOCK_THREADS 512
+#define PM_BLOCK_THREADS 1024
 #endif
 #ifndef PM_MIN_BLOCKS
-#define PM_MIN_BLOCKS 2
+#define PM_MIN_BLOCKS 1
 #endif
+constexpr int block_threads(int W) { return W == 1 ? PM_BLOCK_THREADS : 256; }
+constexpr int min_blocks(int W) { return W == 1 ? PM_MIN_BLOCKS : 2; }
+
 template <int W>
-__global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_kernel(const KernelArgs args) {
+__global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_kernel(const KernelArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int CW = 32 * W;  // conformer slots per row
   const int lane = threadIdx.x & 31;
@@ -499,7 +506,7 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
                   if ((tm >> sm.ntype[mn]) & 1u) mlist[mo++] = (uint8_t)mn;
                 }
               }
-              rec[ro++] = make_uint2((uint32_t)(nb + (i - c0)) | ((uint32_t)M << 8) | (x << 16), packed);
+              rec[ro++] = make_uint2((uint32_t)(nb + (i - c0)) | ((uint32_t)(M - 1) << 8) | (x << 16), packed);
             }
           }
           rec_used += trec;
@@ -645,12 +652,12 @@ __global__ void __launch_bounds__(PM_BLOCK_THREADS, PM_MIN_BLOCKS) pmnet_score_k
                   bool dead = false;
                   for (int a = 0; a < cnt1; ++a) {
                     const uint2 r1 = rec[off1 + a];
-                    const int drow = rec_node(r1) * NL;
+                    const float* const drow = dist_l + (unsigned)(rec_node(r1) * NL * CW);
                     for (int b = 0; b < cnt2; ++b) {
                       const uint2 r2 = rec[off2 + b];
                       float d[W];
 #pragma unroll
-                      for (int w = 0; w < W; ++w) d[w] = dist_l[(drow + rec_node(r2)) * CW + 32 * w];
+                      for (int w = 0; w < W; ++w) d[w] = drow[(unsigned)(rec_node(r2) * CW + 32 * w)];
                       pair_term<W>(sm, mlist, d, r1, r2, sc, nfail);
                     }
                     // every conformer already failed: the pair is invalid whatever follows
@@ -984,20 +991,21 @@ int sm_count_cached() {
   return n;
 }
 
+// 32-conformer words per ligand for a launch that must handle up to `max_conformers` conformers
+int conf_words(int max_conformers) { return max_conformers <= 32 ? 1 : (max_conformers <= 64 ? 2 : 4); }
+
 void resolve_cfg(const PmScoreConfig* in, PmScoreConfig* out, bool query_device) {
   PmScoreConfig c = {0, 0, 0, 0};
   if (in) c = *in;
-  constexpr int kMaxWarps = PM_BLOCK_THREADS / 32;
-  if (c.warps_per_block <= 0) c.warps_per_block = kMaxWarps;
-  if (c.warps_per_block > kMaxWarps) c.warps_per_block = kMaxWarps;
-  if (c.blocks <= 0) c.blocks = PM_MIN_BLOCKS * (query_device ? sm_count_cached() : 148);
-  if (c.scratch_rows <= 0) c.scratch_rows = 8192;
   if (c.max_conformers <= 0) c.max_conformers = 32;
+  const int W = conf_words(c.max_conformers);
+  const int max_warps = block_threads(W) / 32;
+  if (c.warps_per_block <= 0) c.warps_per_block = max_warps;
+  if (c.warps_per_block > max_warps) c.warps_per_block = max_warps;
+  if (c.blocks <= 0) c.blocks = min_blocks(W) * (query_device ? sm_count_cached() : 148);
+  if (c.scratch_rows <= 0) c.scratch_rows = 8192;
   *out = c;
 }
-
-// 32-conformer words per ligand for a launch that must handle up to `max_conformers` conformers
-int conf_words(int max_conformers) { return max_conformers <= 32 ? 1 : (max_conformers <= 64 ? 2 : 4); }
 
 }  // namespace
 

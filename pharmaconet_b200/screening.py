@@ -260,6 +260,72 @@ class Screener:
         return ScreenResult(ks, ki, host_scores, ids, n_mine, n_conf, int(len(over)), launches)
 
 
+def screen_models(
+    models,
+    batch: DeviceLigandBatch,
+    host_lib: LigandBatch | None = None,
+    weights: dict[str, float] | None = None,
+    k: int = 1000,
+    config: ScoreConfig | None = None,
+    id_base: int = 0,
+    gather: bool = True,
+    keep_scores: bool = False,
+) -> list[ScreenResult]:
+    """Screen ONE device-resident library shard against MANY pharmacophore models (BASELINE configs[4]: the models
+    of a batch of pockets against the same library; the reference runs `screening.py` once per model).
+
+    The library stays in HBM; every model is one scoring launch plus a top-k, alternating between two streams with
+    their own scratch so that the long-ligand tail of one model's persistent grid overlaps the start of the next.
+    There is no host synchronisation until all models are enqueued. Ligands whose pair table overflowed the per-warp
+    scratch are re-run with the roomy configuration when `host_lib` (the same shard on the host) is given; otherwise
+    their count is reported in `n_overflow` and their score is 0.
+    """
+    dev = batch.device
+    cfg = config or ScoreConfig()
+    dms = [DeviceModel(m if isinstance(m, PackedModel) else m.packed, dev) for m in models]
+    if not dms:
+        return []
+    main = torch.cuda.current_stream(dev)
+    start = torch.cuda.Event()
+    start.record(main)
+    streams = [torch.cuda.Stream(dev) for _ in range(min(2, len(dms)))]
+    spaces = []
+    for i in range(len(streams)):
+        need = max(workspace_bytes(dm, cfg, batch.max_conformers) for dm in dms[i :: len(streams)])
+        spaces.append(torch.empty(need, dtype=torch.uint8, device=dev))
+    outs = []
+    for i, dm in enumerate(dms):
+        st = streams[i % len(streams)]
+        if i < len(streams):
+            st.wait_event(start)
+        with torch.cuda.stream(st):  # outputs are allocated on the stream that writes them
+            o = score_batch(dm, batch, weights, cfg, stream=st, workspace=spaces[i % len(streams)])
+            ks, ki = topk(o["scores"], k, id_base, stream=st)
+        for t in (o["scores"], o["status"], ks, ki):
+            t.record_stream(main)  # read on the caller's stream below
+        outs.append((o, ks, ki))
+    for st in streams:
+        main.wait_stream(st)
+    results = []
+    for dm, (o, ks, ki) in zip(dms, outs):
+        over = torch.nonzero(o["status"] == _abi.LIG_OVERFLOW).flatten()  # (first host sync of the call)
+        n_over = int(over.numel())
+        launches = 3
+        if n_over and host_lib is not None:
+            sub = host_lib.select(over.cpu().numpy())
+            o2 = score_batch(dm, DeviceLigandBatch.from_host(sub, dev), weights, big_config(dm))
+            o["scores"][over] = o2["scores"]
+            ks, ki = topk(o["scores"], k, id_base)
+            launches += 3
+        if gather:
+            ks, ki = gather_topk(ks, ki, k)
+        results.append(
+            ScreenResult(ks, ki, o["scores"] if keep_scores else None, None, batch.n_ligands, batch.n_conformers_total,
+                         n_over, launches)
+        )  # fmt: skip
+    return results
+
+
 def write_csv(path: str, names, scores) -> None:
     """The reference's output format (screening.py:70-75): `path,score`, descending by score."""
     order = np.lexsort((np.arange(len(scores)), -np.asarray(scores, dtype=np.float64)))

@@ -218,3 +218,19 @@ def test_ligand_without_pharmacophores_scores_zero():
     assert out["scores"][1] == 0.0 and out["scores"][3] == 0.0  # graph_match.py:95-96
     assert np.array_equal(out["status"], o["status"]) and out["status"][1] == _abi.LIG_EMPTY
     assert rel_err(out["scores"][[0, 2, 4]], o["scores"][[0, 2, 4]]).max() <= REL_TOL
+
+
+def test_screen_models_equals_one_screener_per_model():
+    """Many models against one resident library (BASELINE configs[4]) == one Screener per model."""
+    from pharmaconet_b200 import screening
+
+    lib = LigandBatch.from_typed(synthetic.make_ligands(3000, 16, seed=77))
+    db = scoring.DeviceLigandBatch.from_host(lib, "cuda:0")
+    models = [load_case(n)["model"] for n in ("syn0_c8", "sparse_c16", "xbond_c4")]
+    res = screening.screen_models(models, db, host_lib=lib, k=50, keep_scores=True)
+    assert len(res) == 3
+    for m, r in zip(models, res):
+        one = screening.Screener(m, "cuda:0", k=50).screen_device(db)
+        assert torch.equal(r.topk_ids, one.topk_ids)
+        assert torch.equal(r.topk_scores, one.topk_scores)
+        assert torch.equal(r.scores, one.scores)
