@@ -151,11 +151,40 @@ def typed_ligand_from_pbmol(pbmol, atom_positions, conformer_axis: int | None = 
     return TypedLigand(table.atomic_nums, table.neighbors, type_atoms(table), pos)
 
 
-def typed_ligand_from_file(filename, num_conformers: int | None = None) -> TypedLigand:
-    """ligand.py:63-84: every molecule record of the file is one conformer of the same ligand."""
-    pybel, _ = _openbabel()
+_warned_builtin = False
+
+
+def typed_ligand_from_file(filename, num_conformers: int | None = None, perception: str = "auto") -> TypedLigand:
+    """ligand.py:63-84: every molecule record of the file is one conformer of the same ligand.
+
+    perception: "openbabel" (the reference's), "builtin" (`pharmaconet_b200.sdf`: toolkit-free, approximate,
+    `.sdf` only) or "auto" (OpenBabel when importable, else the built-in reader for `.sdf`)."""
     ext = os.path.splitext(str(filename))[1]
     assert ext in [".sdf", ".pdb", ".mol2"]
+    if perception not in ("auto", "openbabel", "builtin"):
+        raise ValueError(f"unknown perception mode {perception!r}")
+    if perception != "openbabel" and ext == ".sdf":
+        use_builtin = perception == "builtin"
+        if not use_builtin:
+            try:
+                _openbabel()
+            except ImportError:
+                use_builtin = True
+        if use_builtin:
+            global _warned_builtin
+            if perception == "auto" and not _warned_builtin:
+                import warnings
+
+                warnings.warn(
+                    "OpenBabel is not installed: typing .sdf ligands with the built-in approximate perception "
+                    "(pharmaconet_b200.sdf); pharmacophore types may differ from the reference's",
+                    stacklevel=2,
+                )
+                _warned_builtin = True
+            from .sdf import typed_ligand_from_sdf
+
+            return typed_ligand_from_sdf(str(filename), num_conformers)
+    pybel, _ = _openbabel()
     it = pybel.readfile(ext[1:], str(filename))
     mols = list(it if num_conformers is None else itertools.islice(it, num_conformers))
     base = mols[0]

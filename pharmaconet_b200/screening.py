@@ -107,7 +107,8 @@ class Screener:
         weights: dict[str, float] | None = None,
         k: int = 1000,
         config: ScoreConfig | None = None,
-        block_ligands: int = 65536,
+        block_ligands: int = 131072,
+        n_slots: int = 2,
     ):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
@@ -118,6 +119,7 @@ class Screener:
         self.k = int(k)
         self.config = config or ScoreConfig()
         self.block_ligands = int(block_ligands)
+        self.n_slots = max(2, int(n_slots))  # device staging buffers (each with its own stream and scratch)
         self._copy_stream = torch.cuda.Stream(self.device)
         self._slots: list[_Slot] | None = None
         self._slot_caps: dict[str, int] | None = None
@@ -174,7 +176,7 @@ class Screener:
         if self._slots is not None and all(self._slot_caps[k] >= caps[k] for k in caps):
             return
         dtypes = {k: torch.from_numpy(v[:0]).dtype for k, v in lib.arrays().items()}
-        self._slots = [_Slot(caps, dtypes, self.device) for _ in range(2)]
+        self._slots = [_Slot(caps, dtypes, self.device) for _ in range(self.n_slots)]
         self._slot_caps = caps
 
     def screen_host(
@@ -184,6 +186,13 @@ class Screener:
         dev = self.device
         blocks = shard_blocks(lib.num_ligands, rank, world, self.block_ligands)
         n_mine = sum(b - a for a, b in blocks)
+        # ramp-up: nothing overlaps the copy of the very first span, so the first block is cut into growing pieces
+        # (1/8, 1/8, 1/4, 1/2) - the kernel starts after an eighth of a block has arrived
+        if blocks and blocks[0][1] - blocks[0][0] >= 8192:
+            a0, b0 = blocks[0]
+            n0 = b0 - a0
+            cuts = [a0, a0 + n0 // 8, a0 + n0 // 4, a0 + n0 // 2, b0]
+            blocks = [(cuts[i], cuts[i + 1]) for i in range(4)] + blocks[1:]
         scores = torch.empty(n_mine, dtype=torch.float32, device=dev)
         status = torch.empty(n_mine, dtype=torch.int32, device=dev)
         cand_s, cand_i = [], []
@@ -196,14 +205,13 @@ class Screener:
         start.record(main)
         need = workspace_bytes(self.model, self.config, max(1, lib.max_conformers))
         pos = 0
-        spans = []
         for it, (a, b) in enumerate(blocks):
-            slot = self._slots[it % 2]
+            slot = self._slots[it % self.n_slots]
             if slot.workspace is None or slot.workspace.numel() < need:
                 slot.workspace = torch.empty(need, dtype=torch.uint8, device=dev)
             sl, bases = self._block_slices(lib, a, b)
             with torch.cuda.stream(self._copy_stream):
-                if it < 2:
+                if it < self.n_slots:
                     self._copy_stream.wait_event(start)
                 else:
                     self._copy_stream.wait_event(slot.free)
@@ -217,24 +225,22 @@ class Screener:
             nc = int(lib.n_conf[a:b].sum())
             n_conf += nc
             db = DeviceLigandBatch(views, nb, nc, bases, max_conformers=int(lib.n_conf[a:b].max()))
-            if it < 2:
+            if it < self.n_slots:
                 slot.stream.wait_event(start)
             slot.stream.wait_event(slot.ready)
             self._timed_score(
                 db, out_scores=scores[pos : pos + nb], out_status=status[pos : pos + nb],
                 stream=slot.stream, workspace=slot.workspace,
             )  # fmt: skip
+            # the span's own top-k follows on the same stream, under the next span's kernel
+            ks, ki = topk(scores[pos : pos + nb], self.k, a, stream=slot.stream)
+            cand_s.append(ks)
+            cand_i.append(ki)
             slot.free.record(slot.stream)
-            spans.append((pos, nb, a))
-            launches += 1
+            launches += 3
             pos += nb
         for slot in (self._slots or [])[: len(blocks)]:
             main.wait_event(slot.free)
-        for p0, nb, a in spans:
-            ks, ki = topk(scores[p0 : p0 + nb], self.k, a)
-            cand_s.append(ks)
-            cand_i.append(ki)
-            launches += 2
         ids = np.concatenate([np.arange(a, b, dtype=np.int64) for a, b in blocks]) if blocks else np.zeros(0, np.int64)
         # ligands whose pair table overflowed the per-warp scratch: re-run them with the roomy configuration
         st = status.cpu().numpy()

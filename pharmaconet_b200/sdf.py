@@ -1,0 +1,264 @@
+"""Toolkit-free SDF reader with APPROXIMATE chemistry perception (screening plumbing without OpenBabel).
+
+The reference types ligands with OpenBabel (`src/pmnet/scoring/ligand.py:17-84`, `ligand_utils.py:25-88`):
+hydrogen-bond donors / acceptors, SSSR aromatic rings and hybridisation are OpenBabel's perception, i.e.
+third-party arithmetic that is not in the reference repository and is not installed here.
+This module restates the *published rules of thumb* behind those queries on the connection table of an MDL
+V2000 file, so that `screening.py` can run on real `.sdf` libraries (BASELINE configs[0], the reference's
+`examples/library.tar`) without any toolkit:
+
+* one file = one ligand, every record one conformer (ligand.py:63-84); hydrogens are stripped;
+* donors: N / O with at least one attached hydrogen;
+* acceptors: O (neutral or anionic, not in an aromatic ring); N that is neutral, not amide / sulfonamide, not bonded
+  to an aromatic ring while carrying hydrogens or three substituents (aniline-like), not an aromatic N with three
+  connections (pyrrole-like), and has fewer than four bonds;
+* aromatic rings: smallest rings (size 5-7) of the bond graph whose atoms are all sp2-capable and hold 4n+2 pi
+  electrons in a Kekule structure (or are written with bond type 4);
+* hybridisation: 1 / 2 / 3 from the bond orders; N next to C=O / C=S / an aromatic ring counts as planar (2).
+
+Where OpenBabel is importable the callers use it instead (`ligand_typing.typed_ligand_from_file`). Typing parity
+with the reference is UNPINNED either way; the scoring parity tests feed the same typed ligands to both sides.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .ligand import TypedLigand
+from .ligand_typing import AtomTable, type_atoms
+
+_Z = {
+    "H": 1, "D": 1, "B": 5, "C": 6, "N": 7, "O": 8, "F": 9, "Si": 14, "P": 15, "S": 16, "Cl": 17, "Se": 34, "Br": 35,
+    "I": 53, "Na": 11, "K": 19, "Li": 3, "Mg": 12, "Ca": 20, "Zn": 30, "Fe": 26, "Cu": 29, "As": 33,
+}  # fmt: skip
+_V2000_CHARGE = {0: 0, 1: 3, 2: 2, 3: 1, 4: 0, 5: -1, 6: -2, 7: -3}
+
+
+@dataclass
+class MolRecord:
+    atomic_nums: list[int]
+    coords: np.ndarray  # float64 [n, 3]
+    bonds: list[tuple[int, int, int]]  # (i, j, order), 0-based; order 4 = aromatic
+    charges: list[int]
+
+
+def parse_sdf(text: str, max_records: int | None = None) -> list[MolRecord]:
+    """All V2000 connection tables of an SD file."""
+    out: list[MolRecord] = []
+    for block in text.split("$$$$"):
+        lines = block.lstrip("\n").splitlines()
+        if len(lines) < 4:
+            continue
+        # the counts line is the 4th line of a molfile; tolerate a missing leading blank line
+        ci = next((k for k in range(min(6, len(lines))) if lines[k].rstrip().endswith("V2000")), None)
+        if ci is None:
+            raise ValueError("only MDL V2000 records are supported")
+        na, nb = int(lines[ci][0:3]), int(lines[ci][3:6])
+        z, xyz, chg = [], [], []
+        for ln in lines[ci + 1 : ci + 1 + na]:
+            xyz.append((float(ln[0:10]), float(ln[10:20]), float(ln[20:30])))
+            sym = ln[31:34].strip()
+            z.append(_Z.get(sym, _Z.get(sym.capitalize(), 0)))
+            c = ln[36:39].strip()
+            chg.append(_V2000_CHARGE.get(int(c), 0) if c else 0)
+        bonds = []
+        for ln in lines[ci + 1 + na : ci + 1 + na + nb]:
+            bonds.append((int(ln[0:3]) - 1, int(ln[3:6]) - 1, int(ln[6:9])))
+        for ln in lines[ci + 1 + na + nb :]:
+            if ln.startswith("M  CHG"):
+                n = int(ln[6:9])
+                for k in range(n):
+                    a = int(ln[10 + 8 * k : 13 + 8 * k]) - 1
+                    chg[a] = int(ln[14 + 8 * k : 17 + 8 * k])
+            elif ln.startswith("M  END"):
+                break
+        out.append(MolRecord(z, np.asarray(xyz, dtype=np.float64), bonds, chg))
+        if max_records is not None and len(out) >= max_records:
+            break
+    return out
+
+
+def _smallest_rings(n: int, adj: list[list[int]], max_size: int = 7) -> list[tuple[int, ...]]:
+    """Smallest ring through every ring bond (a superset of the SSSR's 5-7 rings for drug-like molecules), unique."""
+    rings: set[tuple[int, ...]] = set()
+    seen_keys: set[frozenset] = set()
+    for a in range(n):
+        for b in adj[a]:
+            if b < a:
+                continue
+            # shortest path a -> b that does not use the bond a-b
+            prev = {a: -1}
+            frontier = [a]
+            found = False
+            depth = 0
+            while frontier and not found and depth < max_size - 1:
+                depth += 1
+                nxt = []
+                for u in frontier:
+                    for v in adj[u]:
+                        if (u == a and v == b) or v in prev:
+                            continue
+                        prev[v] = u
+                        if v == b:
+                            found = True
+                            break
+                        nxt.append(v)
+                    if found:
+                        break
+                frontier = nxt
+            if not found:
+                continue
+            path = [b]
+            while path[-1] != a:
+                path.append(prev[path[-1]])
+            key = frozenset(path)
+            if len(path) <= max_size and key not in seen_keys:
+                seen_keys.add(key)
+                rings.add(tuple(path))
+    return sorted(rings, key=lambda r: (len(r), sorted(r)))
+
+
+def perceive(rec: MolRecord) -> tuple[AtomTable, list[int]]:
+    """AtomTable of the hydrogen-stripped molecule + the indices of the kept (heavy) atoms in the record."""
+    n_all = len(rec.atomic_nums)
+    heavy = [i for i in range(n_all) if rec.atomic_nums[i] != 1]
+    new = {old: k for k, old in enumerate(heavy)}
+    n = len(heavy)
+    z = [rec.atomic_nums[i] for i in heavy]
+    charge = [rec.charges[i] for i in heavy]
+    nbrs: list[list[int]] = [[] for _ in range(n)]
+    order: dict[tuple[int, int], int] = {}
+    n_h = [0] * n
+    for i, j, o in rec.bonds:
+        hi, hj = rec.atomic_nums[i] == 1, rec.atomic_nums[j] == 1
+        if hi and hj:
+            continue
+        if hi or hj:
+            n_h[new[j if hi else i]] += 1
+            continue
+        a, b = new[i], new[j]
+        nbrs[a].append(b)
+        nbrs[b].append(a)
+        order[(a, b)] = order[(b, a)] = o
+    for a in range(n):
+        nbrs[a].sort()
+
+    def bo(a, b):
+        return order[(a, b)]
+
+    has_double = [any(bo(a, b) == 2 for b in nbrs[a]) for a in range(n)]
+    has_triple = [any(bo(a, b) == 3 for b in nbrs[a]) for a in range(n)]
+    n_double = [sum(bo(a, b) == 2 for b in nbrs[a]) for a in range(n)]
+
+    # ---- aromatic rings
+    rings = _smallest_rings(n, nbrs)
+    in_ring = [False] * n
+    for r in rings:
+        for a in r:
+            in_ring[a] = True
+    aromatic_rings: list[tuple[int, ...]] = []
+    for r in rings:
+        if not 5 <= len(r) <= 7:
+            continue
+        ring = set(r)
+        k = len(r)
+        if all(bo(r[i], r[(i + 1) % k]) == 4 for i in range(k)):
+            aromatic_rings.append(tuple(r))
+            continue
+        pi = 0
+        ok = True
+        for a in r:
+            dbl = [b for b in nbrs[a] if bo(a, b) in (2, 4)]
+            if dbl:
+                b = dbl[0]
+                if b in ring or in_ring[b]:
+                    pi += 1  # endocyclic double bond (possibly of a fused ring)
+                elif z[b] in (7, 8, 16) and z[a] == 6:
+                    pi += 0  # exocyclic C=O / C=N / C=S: empty p orbital
+                else:
+                    ok = False
+            elif z[a] in (7, 8, 16) and len(nbrs[a]) + n_h[a] <= 3 and charge[a] <= 0:
+                pi += 2  # lone pair
+            elif z[a] == 6 and charge[a] == -1:
+                pi += 2
+            elif z[a] in (5,) or (z[a] == 6 and charge[a] == 1):
+                pi += 0
+            else:
+                ok = False
+            if not ok:
+                break
+        if ok and pi % 4 == 2:
+            aromatic_rings.append(tuple(r))
+    arom_atom = [False] * n
+    for r in aromatic_rings:
+        for a in r:
+            arom_atom[a] = True
+
+    # ---- hybridisation (OpenBabel GetHyb: 1, 2, 3)
+    def conj_nb(a):  # neighbour that makes an N lone pair planar
+        return any(arom_atom[b] or any(bo(b, c) == 2 and z[c] in (8, 16, 7) for c in nbrs[b]) for b in nbrs[a])
+
+    hyb = []
+    for a in range(n):
+        if has_triple[a] or n_double[a] >= 2:
+            hyb.append(1)
+        elif has_double[a] or arom_atom[a]:
+            hyb.append(2)
+        elif z[a] == 7 and conj_nb(a):
+            hyb.append(2)
+        else:
+            hyb.append(3)
+
+    # ---- donors / acceptors
+    def is_amide_like_n(a):
+        for b in nbrs[a]:
+            if z[b] in (6, 16, 15) and any(bo(b, c) == 2 and z[c] in (8, 16) for c in nbrs[b] if c != a):
+                return True
+        return False
+
+    is_donor = [z[a] in (7, 8) and n_h[a] > 0 for a in range(n)]
+    is_acceptor = []
+    for a in range(n):
+        acc = False
+        if z[a] == 8:
+            acc = charge[a] <= 0 and not arom_atom[a]
+        elif z[a] == 7:
+            total = len(nbrs[a]) + n_h[a]
+            acc = charge[a] <= 0 and total < 4 and not is_amide_like_n(a)
+            if acc and arom_atom[a] and total == 3:
+                acc = False  # pyrrole-type
+            if acc and not arom_atom[a] and hyb[a] == 2 and not has_double[a]:
+                acc = False  # aniline-type / conjugated amine: the lone pair is delocalised
+        is_acceptor.append(acc)
+
+    table = AtomTable(
+        atomic_nums=z,
+        neighbors=nbrs,
+        explicit_degree=[len(x) for x in nbrs],
+        heavy_degree=[len(x) for x in nbrs],
+        hyb=hyb,
+        is_acceptor=is_acceptor,
+        is_donor=is_donor,
+        aromatic_rings=aromatic_rings,
+    )
+    return table, heavy
+
+
+def typed_ligand_from_sdf(path: str, num_conformers: int | None = None) -> TypedLigand:
+    """Every record of the file is one conformer of the same ligand (ligand.py:63-84)."""
+    with open(path) as f:
+        recs = parse_sdf(f.read(), num_conformers)
+    if not recs:
+        raise ValueError(f"{path}: no molecule records")
+    table, heavy = perceive(recs[0])
+    coords = []
+    for r in recs:
+        if len(r.atomic_nums) != len(recs[0].atomic_nums):
+            raise ValueError(f"{path}: conformer records differ in atom count")
+        coords.append(r.coords[heavy].astype(np.float32))
+    pos = np.stack(coords, axis=1)  # [atoms, conformers, 3]
+    lig = TypedLigand(table.atomic_nums, table.neighbors, type_atoms(table), pos)
+    lig.name = str(path)
+    return lig

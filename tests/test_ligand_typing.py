@@ -69,5 +69,9 @@ def test_file_entry_points_fail_loudly_without_openbabel():
     try:
         import openbabel  # noqa: F401
     except ImportError:
+        # .mol2 / .pdb and an explicit request for the reference's perception need the toolkit; .sdf falls back to
+        # the built-in approximate reader (tests/test_sdf.py)
         with pytest.raises(ImportError, match="OpenBabel"):
-            lt.typed_ligand_from_file("x.sdf")
+            lt.typed_ligand_from_file("x.mol2")
+        with pytest.raises(ImportError, match="OpenBabel"):
+            lt.typed_ligand_from_file("x.sdf", perception="openbabel")

@@ -12,6 +12,10 @@ from pharmaconet_b200.packing import LigandBatch
 def test_host_featuriser_reproduces_reference_graphs(name):
     # golden lig_* arrays were packed from the reference's own LigandGraph objects (ligand.py:110-259)
     c = load_case(name)
+    if "source" in c["gen_kwargs"]:
+        # real molecules of the reference's examples/library.tar (not shipped): oracle/make_golden_examples.py
+        # asserted the same equality when it wrote the fixture
+        pytest.skip("fixture built from files outside the repository")
     ligs = synthetic.make_ligands(**c["gen_kwargs"])
     own = LigandBatch.from_typed(ligs)
     for k, v in c["batch"].arrays().items():

@@ -234,3 +234,19 @@ def test_screen_models_equals_one_screener_per_model():
         assert torch.equal(r.topk_ids, one.topk_ids)
         assert torch.equal(r.topk_scores, one.topk_scores)
         assert torch.equal(r.scores, one.scores)
+
+
+def test_streamed_screening_ramp_up_spans():
+    """First block cut into growing spans (1/8, 1/8, 1/4, 1/2): same scores, ids and top-k as one launch."""
+    from pharmaconet_b200 import screening
+
+    c = load_case("syn0_c8")
+    batch = LigandBatch.from_typed(synthetic.make_ligands(9000, 4, seed=91))
+    whole = _run(c["model"], batch, None)["scores"]
+    scr = screening.Screener(c["model"], "cuda:0", k=64, block_ligands=8192)
+    res = scr.screen_host(screening.pin_library(batch))
+    assert np.array_equal(res.ids, np.arange(9000))
+    assert np.array_equal(res.scores, whole)
+    order = np.lexsort((np.arange(9000), -whole.astype(np.float64)))[:64]
+    assert np.array_equal(res.topk_ids.cpu().numpy(), order)
+    assert res.launches == 3 * 5  # four ramp spans + the second block, each: kernel + id fill + top-k write-out

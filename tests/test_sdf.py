@@ -1,0 +1,115 @@
+"""Toolkit-free SDF reader (pharmaconet_b200/sdf.py): parsing and the approximate perception rules on hand-made
+molecules. Typing parity with OpenBabel is unpinned (the toolkit is absent); these tests pin the stated rules."""
+
+import numpy as np
+
+from pharmaconet_b200 import sdf
+from pharmaconet_b200.ligand_typing import type_atoms, typed_ligand_from_file
+
+
+def molblock(atoms, bonds, charges=None):
+    """atoms: [(symbol, x, y, z)], bonds: [(i, j, order)] 1-based."""
+    lines = ["", "  handmade", "", f"{len(atoms):3d}{len(bonds):3d}  0  0  0  0  0  0  0  0999 V2000"]
+    for s, x, y, z in atoms:
+        lines.append(f"{x:10.4f}{y:10.4f}{z:10.4f} {s:<3s} 0  0  0  0  0  0  0  0  0  0  0  0")
+    for i, j, o in bonds:
+        lines.append(f"{i:3d}{j:3d}{o:3d}  0")
+    if charges:
+        lines.append(f"M  CHG{len(charges):3d}" + "".join(f"{a:4d}{c:4d}" for a, c in charges))
+    lines.append("M  END")
+    return "\n".join(lines) + "\n$$$$\n"
+
+
+def ring(n, syms, orders, extra_atoms=(), extra_bonds=()):
+    atoms = [(syms[i], np.cos(2 * np.pi * i / n) * 1.4, np.sin(2 * np.pi * i / n) * 1.4, 0.0) for i in range(n)]
+    bonds = [(i + 1, (i + 1) % n + 1, orders[i]) for i in range(n)]
+    atoms += list(extra_atoms)
+    bonds += list(extra_bonds)
+    return atoms, bonds
+
+
+def types_of(block):
+    table, heavy = sdf.perceive(sdf.parse_sdf(block)[0])
+    out = {}
+    for t, atoms, _ in type_atoms(table):
+        out.setdefault(t, []).append(atoms)
+    return table, out
+
+
+def test_benzene_is_one_aromatic_ring_of_hydrophobic_carbons():
+    atoms, bonds = ring(6, "CCCCCC", [2, 1, 2, 1, 2, 1])
+    atoms += [("H", 2.4 * np.cos(2 * np.pi * i / 6), 2.4 * np.sin(2 * np.pi * i / 6), 0.0) for i in range(6)]
+    bonds += [(i + 1, 7 + i, 1) for i in range(6)]
+    table, t = types_of(molblock(atoms, bonds))
+    assert len(table.atomic_nums) == 6  # hydrogens stripped
+    assert t["Aromatic"] == [(0, 1, 2, 3, 4, 5)]
+    assert sorted(t["Hydrophobic"]) == list(range(6))
+    assert "HBond_donor" not in t and "HBond_acceptor" not in t
+
+
+def test_cyclohexane_and_cyclohexene_are_not_aromatic():
+    for orders in ([1] * 6, [2, 1, 1, 1, 1, 1], [2, 1, 2, 1, 1, 1]):
+        atoms, bonds = ring(6, "CCCCCC", orders)
+        _, t = types_of(molblock(atoms, bonds))
+        assert "Aromatic" not in t
+
+
+def test_pyridine_n_accepts_pyrrole_nh_donates_furan_o_is_silent():
+    atoms, bonds = ring(6, "NCCCCC", [2, 1, 2, 1, 2, 1])
+    _, t = types_of(molblock(atoms, bonds))
+    assert t["Aromatic"] == [(0, 1, 2, 3, 4, 5)] and t["HBond_acceptor"] == [0] and "HBond_donor" not in t
+    atoms, bonds = ring(5, "NCCCC", [1, 2, 1, 2, 1], [("H", 2.4, 0.0, 0.0)], [(1, 6, 1)])
+    _, t = types_of(molblock(atoms, bonds))
+    assert t["Aromatic"] == [(0, 1, 2, 3, 4)] and t["HBond_donor"] == [0] and "HBond_acceptor" not in t
+    atoms, bonds = ring(5, "OCCCC", [1, 2, 1, 2, 1])
+    _, t = types_of(molblock(atoms, bonds))
+    assert t["Aromatic"] == [(0, 1, 2, 3, 4)] and "HBond_acceptor" not in t
+
+
+def test_naphthalene_has_two_aromatic_rings_in_either_kekule_form():
+    # atoms 1-10, fusion bond 5-10 ... ring A: 1 2 3 4 5 10, ring B: 5 6 7 8 9 10
+    atoms = [("C", float(i), 0.0, 0.0) for i in range(10)]
+    ring_bonds = [(1, 2), (2, 3), (3, 4), (4, 5), (5, 10), (10, 1), (5, 6), (6, 7), (7, 8), (8, 9), (9, 10)]
+    for doubles in ({(1, 2), (3, 4), (5, 10), (6, 7), (8, 9)}, {(10, 1), (2, 3), (4, 5), (6, 7), (8, 9)}):
+        bonds = [(i, j, 2 if (i, j) in doubles else 1) for i, j in ring_bonds]
+        _, t = types_of(molblock(atoms, bonds))
+        assert sorted(t["Aromatic"]) == [(0, 1, 2, 3, 4, 9), (4, 5, 6, 7, 8, 9)]
+
+
+def test_functional_groups():
+    # acetic acid CH3-C(=O)-OH: carboxylate anion rule, carbonyl O accepts, hydroxyl donates and accepts
+    atoms = [("C", 0, 0, 0), ("C", 1.5, 0, 0), ("O", 2.2, 1.0, 0), ("O", 2.2, -1.0, 0), ("H", 3.1, -1.0, 0)]
+    bonds = [(1, 2, 1), (2, 3, 2), (2, 4, 1), (4, 5, 1)]
+    _, t = types_of(molblock(atoms, bonds))
+    assert t["Anion"] == [(1, 2, 3)] and t["HBond_donor"] == [3] and sorted(t["HBond_acceptor"]) == [2, 3]
+    assert t["Hydrophobic"] == [0]
+    # trimethylamine: tertiary amine cation + acceptor; acetamide N: neither cation nor acceptor, but a donor
+    atoms = [("N", 0, 0, 0), ("C", 1.4, 0, 0), ("C", -0.7, 1.2, 0), ("C", -0.7, -1.2, 0)]
+    _, t = types_of(molblock(atoms, [(1, 2, 1), (1, 3, 1), (1, 4, 1)]))
+    assert t["Cation"] == [0] and t["HBond_acceptor"] == [0]
+    atoms = [("C", 0, 0, 0), ("C", 1.5, 0, 0), ("O", 2.2, 1.0, 0), ("N", 2.2, -1.0, 0), ("H", 3.1, -1.0, 0), ("H", 1.8, -1.9, 0)]
+    _, t = types_of(molblock(atoms, [(1, 2, 1), (2, 3, 2), (2, 4, 1), (4, 5, 1), (4, 6, 1)]))
+    assert "Cation" not in t and t["HBond_acceptor"] == [2] and t["HBond_donor"] == [3]
+    # chlorobenzene-like C-Cl: halogen on carbon; the halogen never accepts
+    _, t = types_of(molblock([("C", 0, 0, 0), ("Cl", 1.7, 0, 0), ("C", -1.5, 0, 0)], [(1, 2, 1), (1, 3, 1)]))
+    assert t["Halogen"] == [1] and "HBond_acceptor" not in t
+
+
+def test_charges_and_conformers(tmp_path):
+    # tetramethylammonium (quaternary N, M  CHG line) written as three conformers
+    atoms = [("N", 0, 0, 0), ("C", 1, 1, 1), ("C", -1, -1, 1), ("C", -1, 1, -1), ("C", 1, -1, -1)]
+    bonds = [(1, k, 1) for k in range(2, 6)]
+    text = ""
+    for shift in (0.0, 0.5, 1.0):
+        text += molblock([(s, x + shift, y, z) for s, x, y, z in atoms], bonds, charges=[(1, 1)])
+    path = tmp_path / "tma.sdf"
+    path.write_text(text)
+    recs = sdf.parse_sdf(text)
+    assert len(recs) == 3 and recs[0].charges[0] == 1
+    lig = typed_ligand_from_file(str(path), perception="builtin")
+    assert lig.num_atoms == 5 and lig.num_conformers == 3
+    assert lig.atom_positions.shape == (5, 3, 3) and lig.atom_positions.dtype == np.float32
+    assert np.allclose(lig.atom_positions[0, :, 0], [0.0, 0.5, 1.0])
+    assert ("Cation", 0, 0) in [tuple(p) for p in lig.pharmacophores]
+    assert not any(p[0] == "HBond_acceptor" for p in lig.pharmacophores)  # N+ with four bonds
+    assert typed_ligand_from_file(str(path), num_conformers=2, perception="builtin").num_conformers == 2
