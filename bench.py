@@ -50,6 +50,10 @@ def parse_args():
     ap.add_argument("--topk", type=int, default=1000)
     ap.add_argument("--block-ligands", type=int, default=131072)
     ap.add_argument("--slots", type=int, default=2, help="device staging slots of the streamed (e2e) leg")
+    ap.add_argument("--no-lpt", action="store_true", help="process ligands in index order instead of longest first")
+    ap.add_argument("--no-ramp", action="store_true", help="streamed leg: do not cut the first block into growing spans")
+    ap.add_argument("--stream-warps", type=int, default=0, help="streamed leg: warps per CTA (0 = library default)")
+    ap.add_argument("--stream-ctas", type=int, default=0, help="streamed leg: CTAs in the grid (0 = library default)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -296,7 +300,11 @@ def main():
     lib = synthetic.make_library_device(args.ligands, args.conformers, args.seed + rank, dev, args.templates)
     n_lig, n_conf = lib.n_ligands, lib.n_conformers_total
     alg_bytes = lib.nbytes() + 4 * n_lig  # every input array once + one fp32 score per ligand
-    scr = screening.Screener(packed, dev, k=args.topk, block_ligands=args.block_ligands, n_slots=args.slots)
+    from pharmaconet_b200.scoring import ScoreConfig
+
+    scfg = ScoreConfig(args.stream_warps, args.stream_ctas, 0) if (args.stream_warps or args.stream_ctas) else None
+    scr = screening.Screener(packed, dev, k=args.topk, block_ligands=args.block_ligands, n_slots=args.slots,
+                             ramp=not args.no_ramp, stream_config=scfg, lpt=not args.no_lpt)
     id_base = rank * n_lig
 
     # ---------------------------------------------------------------- leg 1: library resident in HBM

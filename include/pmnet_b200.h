@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PMNET_ABI_VERSION 1
+#define PMNET_ABI_VERSION 2
 
 /* pharmacophore types, bit positions of every type mask (graph_match.py:32-40) */
 enum {
@@ -102,12 +102,17 @@ typedef struct PmLigandBatch {
   int32_t cluster_base;
   int32_t cnode_base;
   int32_t reserved;
+  /* Optional processing order: [n_ligands] ligand indices (a permutation of 0..n-1), or NULL for index order.
+   * The persistent grid hands ligands to warps in this order; pmnet_cost_order fills it with the ligands sorted by
+   * decreasing expected work, which removes most of the end-of-launch tail (the cost of a ligand varies 100x).
+   * Results do not depend on it: every output array is indexed by ligand. */
+  const int32_t* order;
 } PmLigandBatch;
 
 /* Launch configuration; zero-initialise for defaults. */
 typedef struct PmScoreConfig {
-  int32_t warps_per_block;   /* default 8 */
-  int32_t blocks;            /* default: 2 x SM count */
+  int32_t warps_per_block;   /* default 32 (8 when max_conformers > 32) */
+  int32_t blocks;            /* default: 1 x SM count (2 x when max_conformers > 32) */
   int32_t scratch_rows;      /* per-warp pair-table capacity in rows; default 8192 */
   int32_t max_conformers;    /* largest n_conf in the batch (default 32): selects 1, 2 or 4 conformers per lane;
                                 ligands with more conformers than the launch was sized for get PMNET_LIG_UNSUPPORTED */
@@ -131,6 +136,14 @@ size_t pmnet_score_workspace_bytes(int32_t n_model_nodes, int32_t n_model_cluste
 int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const float* weights,
                       float* out_scores, float* out_conf_scores, int32_t* out_status, uint32_t* out_stats,
                       void* workspace, size_t workspace_bytes, const PmScoreConfig* cfg, void* stream);
+
+/* Longest-processing-time-first order for pmnet_score_batch: out_order[n_ligands] = ligand indices sorted by
+ * decreasing number of (ligand cluster, model cluster) candidate entries over the ligand's first PMNET_MAX_DEPTH
+ * matching clusters (graph_match.py:85-92, 124-137) - the size of the pair table and a good predictor of the tree
+ * size. Stable: ties keep index order. `batch->order` is ignored. workspace: pmnet_order_workspace_bytes(n). */
+size_t pmnet_order_workspace_bytes(int32_t n_ligands);
+int pmnet_cost_order(const PmModel* model, const PmLigandBatch* batch, int32_t* out_order, void* workspace,
+                     size_t workspace_bytes, void* stream);
 
 /* Keep the k best (score, ligand id) pairs of a shard, descending by score, ties by ascending id
  * (screening.py:70 sorts the whole list; a shard only needs its top k for the final merge).

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 PMNET_OK, PMNET_EINVAL, PMNET_EWORKSPACE, PMNET_ELIMIT, PMNET_ECUDA = range(5)
 LIG_OK, LIG_EMPTY, LIG_OVERFLOW, LIG_UNSUPPORTED = range(4)
@@ -49,6 +49,7 @@ class PmLigandBatch(C.Structure):
         ("cluster_base", C.c_int32),
         ("cnode_base", C.c_int32),
         ("reserved", C.c_int32),
+        ("order", C.c_void_p),
     ]
 
 

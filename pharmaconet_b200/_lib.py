@@ -74,6 +74,12 @@ def lib() -> C.CDLL:
         C.POINTER(_abi.PmModel), C.POINTER(_abi.PmLigandBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
         C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(_abi.PmScoreConfig), C.c_void_p,
     ]  # fmt: skip
+    L.pmnet_order_workspace_bytes.restype = C.c_size_t
+    L.pmnet_order_workspace_bytes.argtypes = [C.c_int32]
+    L.pmnet_cost_order.restype = C.c_int
+    L.pmnet_cost_order.argtypes = [
+        C.POINTER(_abi.PmModel), C.POINTER(_abi.PmLigandBatch), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+    ]  # fmt: skip
     L.pmnet_topk_workspace_bytes.restype = C.c_size_t
     L.pmnet_topk_workspace_bytes.argtypes = [C.c_int64, C.c_int32]
     L.pmnet_topk.restype = C.c_int
@@ -125,6 +131,8 @@ EXPORTS = (
     "pmnet_last_error_string",
     "pmnet_score_workspace_bytes",
     "pmnet_score_batch",
+    "pmnet_order_workspace_bytes",
+    "pmnet_cost_order",
     "pmnet_topk_workspace_bytes",
     "pmnet_topk",
     "pmnet_conv3d_k3_c96",

@@ -340,7 +340,10 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
 
   for (;;) {
     unsigned int lig = 0;
-    if (lane == 0) lig = atomicAdd(counter, 1u);
+    if (lane == 0) {
+      lig = atomicAdd(counter, 1u);
+      if (B.order != nullptr && lig < (unsigned)B.n_ligands) lig = (unsigned)B.order[lig];
+    }
     lig = __shfl_sync(kFull, lig, 0);
     if (lig >= (unsigned)B.n_ligands) break;
 
@@ -1099,6 +1102,75 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
   else
     pmnet_score_kernel<4><<<c.blocks, c.warps_per_block * 32, smem, stream>>>(a);
   e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_err(cudaGetErrorString(e));
+    return PMNET_ECUDA;
+  }
+  return PMNET_OK;
+}
+
+// ---------------------------------------------------------------- processing order (longest ligands first)
+// key[i] = number of (level, model cluster) entries of ligand i, exactly the T of the scoring kernel's phase 0
+__global__ void ligand_cost_kernel(const PmModel gm, const PmLigandBatch B, uint32_t* keys, int32_t* idx) {
+  __shared__ uint16_t cnt_by_mask[128];  // model clusters sharing a type with a 7-bit ligand cluster mask
+  for (int m = threadIdx.x; m < 128; m += blockDim.x) {
+    int c = 0;
+    for (int k = 0; k < gm.n_clusters; ++k) c += (gm.cluster_mask[k] & m) ? 1 : 0;
+    cnt_by_mask[m] = (uint16_t)c;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n_ligands) return;
+  const uint8_t* tmask = B.node_type_mask + (B.lig_node_off[i] - B.node_base);
+  const uint8_t* cl_nodes = B.cluster_nodes - B.cnode_base;
+  const int q0 = B.lig_cluster_off[i] - B.cluster_base, q1 = B.lig_cluster_off[i + 1] - B.cluster_base;
+  uint32_t t = 0;
+  int levels = 0;
+  for (int q = q0; q < q1 && levels < kMaxDepth; ++q) {
+    unsigned m = 0;
+    for (int j = B.cluster_node_off[q]; j < B.cluster_node_off[q + 1]; ++j) m |= tmask[cl_nodes[j]];
+    const uint32_t c = cnt_by_mask[m & 127u];
+    t += c;
+    levels += c ? 1 : 0;
+  }
+  keys[i] = t > 65535u ? 65535u : t;
+  idx[i] = i;
+}
+
+static size_t order_sort_bytes(int32_t n) {
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                            (const int32_t*)nullptr, (int32_t*)nullptr, n, 0, 16);
+  return tmp;
+}
+
+size_t pmnet_order_workspace_bytes(int32_t n) {
+  if (n <= 0) return 256;
+  return 3 * align_up((size_t)n * 4, 256) + align_up(order_sort_bytes(n), 256) + 256;
+}
+
+int pmnet_cost_order(const PmModel* model, const PmLigandBatch* batch, int32_t* out_order, void* workspace,
+                     size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!model || !batch || batch->n_ligands < 0 || (batch->n_ligands > 0 && (!out_order || !workspace))) {
+    set_err("pmnet_cost_order: bad argument");
+    return PMNET_EINVAL;
+  }
+  const int32_t n = batch->n_ligands;
+  if (n == 0) return PMNET_OK;
+  if (workspace_bytes < pmnet_order_workspace_bytes(n)) {
+    set_err("pmnet_cost_order: workspace too small");
+    return PMNET_EWORKSPACE;
+  }
+  unsigned char* p = (unsigned char*)workspace;
+  uint32_t* keys = (uint32_t*)p;      p += align_up((size_t)n * 4, 256);
+  uint32_t* keys_out = (uint32_t*)p;  p += align_up((size_t)n * 4, 256);
+  int32_t* idx = (int32_t*)p;         p += align_up((size_t)n * 4, 256);
+  ligand_cost_kernel<<<(n + 255) / 256, 256, 0, stream>>>(*model, *batch, keys, idx);
+  size_t tmp = order_sort_bytes(n);
+  // stable LSD radix sort on the 16 key bits: equal cost keeps index order
+  cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(p, tmp, keys, keys_out, idx, out_order, n, 0, 16, stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_err(cudaGetErrorString(e));
     return PMNET_ECUDA;

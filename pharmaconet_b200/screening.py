@@ -19,7 +19,10 @@ import torch
 
 from . import _abi
 from .packing import LigandBatch, PackedModel
-from .scoring import DeviceLigandBatch, DeviceModel, ScoreConfig, big_config, score_batch, topk, workspace_bytes
+from .scoring import (
+    DeviceLigandBatch, DeviceModel, ScoreConfig, big_config, cost_order, order_workspace_bytes as _lib_order_bytes,
+    score_batch, topk, workspace_bytes,
+)  # fmt: skip
 
 
 def shard_blocks(n_ligands: int, rank: int, world: int, block_ligands: int) -> list[tuple[int, int]]:
@@ -97,6 +100,8 @@ class _Slot:
         # SMs while the previous block's longest ligands are still finishing (the tail of a persistent grid)
         self.stream = torch.cuda.Stream(device)
         self.workspace: torch.Tensor | None = None
+        self.order: torch.Tensor | None = None  # longest-first processing order of the block in flight
+        self.order_ws: torch.Tensor | None = None
 
 
 class Screener:
@@ -109,6 +114,9 @@ class Screener:
         config: ScoreConfig | None = None,
         block_ligands: int = 131072,
         n_slots: int = 2,
+        ramp: bool = True,
+        stream_config: ScoreConfig | None = None,
+        lpt: bool = True,
     ):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
@@ -120,6 +128,11 @@ class Screener:
         self.config = config or ScoreConfig()
         self.block_ligands = int(block_ligands)
         self.n_slots = max(2, int(n_slots))  # device staging buffers (each with its own stream and scratch)
+        self.ramp = bool(ramp)
+        # hand ligands to the warps longest first (scoring.cost_order): removes the end-of-launch tail
+        self.lpt = bool(lpt)
+        # launch shape of the streamed path (None = the library default)
+        self.stream_config = stream_config
         self._copy_stream = torch.cuda.Stream(self.device)
         self._slots: list[_Slot] | None = None
         self._slot_caps: dict[str, int] | None = None
@@ -127,23 +140,28 @@ class Screener:
         self.record_kernel_events = False
         self.kernel_events: list[tuple[torch.cuda.Event, torch.cuda.Event]] = []
 
-    def _timed_score(self, batch, **kw):
+    def _timed_score(self, batch, config=None, **kw):
+        config = config or self.config
         if not self.record_kernel_events:
-            return score_batch(self.model, batch, self.weights, self.config, **kw)
+            return score_batch(self.model, batch, self.weights, config, **kw)
         stream = kw.get("stream") or torch.cuda.current_stream(self.device)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        out = score_batch(self.model, batch, self.weights, self.config, **kw)
+        out = score_batch(self.model, batch, self.weights, config, **kw)
         e1.record(stream)
         self.kernel_events.append((e0, e1))
         return out
 
     # ------------------------------------------------------------------ device-resident shard: one launch
     def screen_device(self, batch: DeviceLigandBatch, id_base: int = 0, gather: bool = True) -> ScreenResult:
+        launches = 3  # scoring kernel + id fill + top-k write-out (the radix sort passes are CUB's)
+        if self.lpt and batch.order is None:
+            # once per resident library and model: the order only depends on topologies and the model's cluster types
+            batch.set_order(cost_order(self.model, batch))
+            launches += 1
         out = self._timed_score(batch)
         n_over = 0
         ks, ki = topk(out["scores"], self.k, id_base)
-        launches = 3  # scoring kernel + id fill + top-k write-out (the radix sort passes are CUB's)
         if gather:
             ks, ki = gather_topk(ks, ki, self.k)
         return ScreenResult(ks, ki, out["scores"], None, batch.n_ligands, batch.n_conformers_total, n_over, launches)
@@ -188,7 +206,7 @@ class Screener:
         n_mine = sum(b - a for a, b in blocks)
         # ramp-up: nothing overlaps the copy of the very first span, so the first block is cut into growing pieces
         # (1/8, 1/8, 1/4, 1/2) - the kernel starts after an eighth of a block has arrived
-        if blocks and blocks[0][1] - blocks[0][0] >= 8192:
+        if self.ramp and blocks and blocks[0][1] - blocks[0][0] >= 8192:
             a0, b0 = blocks[0]
             n0 = b0 - a0
             cuts = [a0, a0 + n0 // 8, a0 + n0 // 4, a0 + n0 // 2, b0]
@@ -203,8 +221,10 @@ class Screener:
         main = torch.cuda.current_stream(dev)
         start = torch.cuda.Event()
         start.record(main)
-        need = workspace_bytes(self.model, self.config, max(1, lib.max_conformers))
+        scfg = self.stream_config or self.config
+        need = workspace_bytes(self.model, scfg, max(1, lib.max_conformers))
         pos = 0
+        spans = []
         for it, (a, b) in enumerate(blocks):
             slot = self._slots[it % self.n_slots]
             if slot.workspace is None or slot.workspace.numel() < need:
@@ -228,19 +248,29 @@ class Screener:
             if it < self.n_slots:
                 slot.stream.wait_event(start)
             slot.stream.wait_event(slot.ready)
+            if self.lpt:
+                if slot.order is None or slot.order.numel() < nb:
+                    slot.order = torch.empty(max(nb, self.block_ligands), dtype=torch.int32, device=dev)
+                    slot.order_ws = torch.empty(
+                        int(_lib_order_bytes(max(nb, self.block_ligands))), dtype=torch.uint8, device=dev
+                    )
+                cost_order(self.model, db, stream=slot.stream, out=slot.order, workspace=slot.order_ws)
+                db.set_order(slot.order)
             self._timed_score(
-                db, out_scores=scores[pos : pos + nb], out_status=status[pos : pos + nb],
+                db, config=scfg, out_scores=scores[pos : pos + nb], out_status=status[pos : pos + nb],
                 stream=slot.stream, workspace=slot.workspace,
             )  # fmt: skip
-            # the span's own top-k follows on the same stream, under the next span's kernel
-            ks, ki = topk(scores[pos : pos + nb], self.k, a, stream=slot.stream)
-            cand_s.append(ks)
-            cand_i.append(ki)
             slot.free.record(slot.stream)
-            launches += 3
+            spans.append((pos, nb, a))
+            launches += 1 + int(self.lpt)
             pos += nb
         for slot in (self._slots or [])[: len(blocks)]:
             main.wait_event(slot.free)
+        for p0, nb, a in spans:
+            ks, ki = topk(scores[p0 : p0 + nb], self.k, a)
+            cand_s.append(ks)
+            cand_i.append(ki)
+            launches += 2
         ids = np.concatenate([np.arange(a, b, dtype=np.int64) for a, b in blocks]) if blocks else np.zeros(0, np.int64)
         # ligands whose pair table overflowed the per-warp scratch: re-run them with the roomy configuration
         st = status.cpu().numpy()
@@ -300,23 +330,30 @@ def screen_models(
         need = max(workspace_bytes(dm, cfg, batch.max_conformers) for dm in dms[i :: len(streams)])
         spaces.append(torch.empty(need, dtype=torch.uint8, device=dev))
     outs = []
+    prev_order = batch.order
+    orders = []  # kept alive until the launches that read them have run
     for i, dm in enumerate(dms):
         st = streams[i % len(streams)]
         if i < len(streams):
             st.wait_event(start)
         with torch.cuda.stream(st):  # outputs are allocated on the stream that writes them
+            # longest ligands first; the order depends on the model's cluster types, so it is per model. The batch
+            # struct is copied into the launch, so re-pointing it between launches is safe.
+            orders.append(cost_order(dm, batch, stream=st))
+            batch.set_order(orders[-1])
             o = score_batch(dm, batch, weights, cfg, stream=st, workspace=spaces[i % len(streams)])
             ks, ki = topk(o["scores"], k, id_base, stream=st)
         for t in (o["scores"], o["status"], ks, ki):
             t.record_stream(main)  # read on the caller's stream below
         outs.append((o, ks, ki))
+    batch.set_order(prev_order)
     for st in streams:
         main.wait_stream(st)
     results = []
     for dm, (o, ks, ki) in zip(dms, outs):
         over = torch.nonzero(o["status"] == _abi.LIG_OVERFLOW).flatten()  # (first host sync of the call)
         n_over = int(over.numel())
-        launches = 3
+        launches = 4
         if n_over and host_lib is not None:
             sub = host_lib.select(over.cpu().numpy())
             o2 = score_batch(dm, DeviceLigandBatch.from_host(sub, dev), weights, big_config(dm))

@@ -249,4 +249,27 @@ def test_streamed_screening_ramp_up_spans():
     assert np.array_equal(res.scores, whole)
     order = np.lexsort((np.arange(9000), -whole.astype(np.float64)))[:64]
     assert np.array_equal(res.topk_ids.cpu().numpy(), order)
-    assert res.launches == 3 * 5  # four ramp spans + the second block, each: kernel + id fill + top-k write-out
+    assert res.launches == 4 * 5  # four ramp spans + the second block, each: cost kernel, scoring, id fill, top-k
+
+
+def test_cost_order_is_a_stable_permutation_and_does_not_change_scores():
+    c = load_case("syn0_c8")
+    dm = scoring.DeviceModel(c["model"], "cuda:0")
+    lib = LigandBatch.from_typed(synthetic.make_ligands(5000, 8, seed=5))
+    db = scoring.DeviceLigandBatch.from_host(lib, "cuda:0")
+    base = scoring.score_batch(dm, db, with_stats=True)
+    order = scoring.cost_order(dm, db)
+    o = order.cpu().numpy()
+    assert np.array_equal(np.sort(o), np.arange(5000))
+    # key = number of (level, model cluster) entries = what the oracle reports as `entries`; descending, stable
+    ent = orc.score(c["model"], lib)["stats"][:, 2].astype(np.int64)
+    assert np.array_equal(o, np.lexsort((np.arange(5000), -ent)))
+    db.set_order(order)
+    ordered = scoring.score_batch(dm, db, with_stats=True)
+    for k in ("scores", "status", "stats"):
+        assert torch.equal(base[k], ordered[k])
+    # a chunk view with un-rebased offsets gets the same relative order
+    from pharmaconet_b200 import screening
+
+    scr = screening.Screener(c["model"], "cuda:0", k=32, block_ligands=1024)
+    assert np.array_equal(scr.screen_host(lib).scores, base["scores"].cpu().numpy())
