@@ -273,3 +273,56 @@ def test_cost_order_is_a_stable_permutation_and_does_not_change_scores():
 
     scr = screening.Screener(c["model"], "cuda:0", k=32, block_ligands=1024)
     assert np.array_equal(scr.screen_host(lib).scores, base["scores"].cpu().numpy())
+
+
+def test_screening_cli_on_sdf_directory(tmp_path):
+    """BASELINE configs[0] plumbing: a directory of multi-conformer .sdf files through screening.py (built-in typing,
+    OpenBabel is absent) equals typing + scoring the same files through the API and the CPU oracle."""
+    import os
+    import subprocess
+    import sys
+
+    from golden_util import GOLDEN
+    from sdf_util import molblock, ring
+
+    from pharmaconet_b200.ligand_typing import typed_ligand_from_file
+
+    rng = np.random.default_rng(3)
+    lib = tmp_path / "lib"
+    lib.mkdir()
+
+    def write(name, atoms, bonds, nconf=3):
+        text = ""
+        for _ in range(nconf):
+            jit = rng.normal(0, 0.15, (len(atoms), 3))
+            text += molblock([(s, x + j[0], y + j[1], z + j[2]) for (s, x, y, z), j in zip(atoms, jit)], bonds)
+        (lib / name).write_text(text)
+
+    # phenol-like ring with a hydroxyl, a pyridine with an amine tail, an acid chain
+    a, b = ring(6, "CCCCCC", [2, 1, 2, 1, 2, 1], [("O", 2.8, 0.0, 0.0), ("H", 3.4, 0.7, 0.0)], [(1, 7, 1), (7, 8, 1)])
+    write("phenol.sdf", a, b)
+    a, b = ring(6, "NCCCCC", [2, 1, 2, 1, 2, 1],
+                [("C", -2.8, 0.0, 0.3), ("N", -3.9, 0.9, 0.5), ("C", -5.2, 0.3, 0.2), ("C", -3.9, 2.3, 0.9), ("C", -4.0, 0.0, 2.0)],
+                [(4, 7, 1), (7, 8, 1), (8, 9, 1), (8, 10, 1), (8, 11, 1)])  # fmt: skip
+    write("pyridine_amine.sdf", a, b, nconf=5)
+    write("acid.sdf", [("C", 0, 0, 0), ("C", 1.5, 0, 0), ("C", 2.3, 1.2, 0), ("O", 3.5, 1.2, 0.4), ("O", 1.7, 2.3, -0.3),
+                       ("H", 2.3, 3.0, -0.2), ("Cl", -1.7, 0.3, 0.2)],
+          [(1, 2, 1), (2, 3, 1), (3, 4, 2), (3, 5, 1), (5, 6, 1), (1, 7, 1)], nconf=4)  # fmt: skip
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "out.csv"
+    subprocess.run(
+        [sys.executable, os.path.join(root, "screening.py"), "-p", os.path.join(GOLDEN, "model_syn0.pm"),
+         "-d", str(lib), "-o", str(out)],
+        check=True, cwd=root, timeout=300,
+    )  # fmt: skip
+    lines = out.read_text().splitlines()
+    assert lines[0] == "path,score" and len(lines) == 4
+    got = {os.path.basename(ln.split(",")[0]): float(ln.split(",")[1]) for ln in lines[1:]}
+    files = sorted(os.listdir(lib))
+    ligs = [typed_ligand_from_file(str(lib / f), perception="builtin") for f in files]
+    batch = LigandBatch.from_typed(ligs)
+    assert list(batch.n_conf) == [4, 3, 5]
+    ref = orc.score(load_case("syn0_c8")["model"], batch)["scores"]
+    assert any(r > 0 for r in ref)
+    for f, r in zip(files, ref):
+        assert abs(got[f] - r) <= REL_TOL * max(abs(r), 1e-12), (f, got[f], r)
