@@ -281,7 +281,16 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the scoring path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = None
     if world > 1:
+        # several ranks stream from host memory at once: keep this rank's pinned pages on its GPU's NUMA node
+        from pharmaconet_b200.affinity import bind_to_gpu
+
+        numa_cpus = bind_to_gpu(local_rank)
+    if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -364,6 +373,7 @@ def main():
             "n_overflow_rerun": r2.n_overflow,
             # sum of the block launches' own durations (they overlap on two streams, so this may exceed the step)
             "kernel_ms_sum_per_step": e2e_kernel_ms, "block_ligands": args.block_ligands, "slots": args.slots,
+            "cpus_bound_rank0": len(numa_cpus) if numa_cpus else None,
         }  # fmt: skip
         same = bool(np.array_equal(r2.scores, gpu_scores.cpu().numpy()))
         e2e["scores_identical_to_resident_leg"] = same

@@ -885,7 +885,9 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
                     for (int w = 0; w < W; ++w) acc[w] += vv[u][w];
                 }
                 const int nmatch = __shfl_sync(kFull, st_nmatch, d) + 1;
-                // the child's candidate masks: parent mask & conformers alive in the child & pair validity
+                // the child's candidate masks: parent mask & conformers alive in the child & pair validity.
+                // (depth d + 1's slot was last read by other lanes while the previous child's subtree was walked)
+                __syncwarp();
                 if (e2a < T) {
 #pragma unroll
                   for (int w = 0; w < W; ++w) nm_[e2a * W + w] = pmv[w] & alive2[w] & vtv[w];

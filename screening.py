@@ -75,6 +75,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
+        from pharmaconet_b200.affinity import bind_to_gpu
+
+        bind_to_gpu(local)  # pinned library pages on the GPU's NUMA node
+    if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     model = PharmacophoreModel.load(args.pharmacophore_model)
     weights = dict(
@@ -83,6 +87,10 @@ def main():
     )  # fmt: skip
     library, names = load_library(args)
     scr = Screener(model, weights=weights, k=min(1000, max(1, library.num_ligands)))
+    if library.coords.nbytes >= (64 << 20):
+        from pharmaconet_b200.screening import pin_library
+
+        library = pin_library(library)  # page-locked: block copies overlap the scoring kernel
     res = scr.screen_host(library, rank=rank, world=world, gather=world > 1)
     scores = np.zeros(library.num_ligands, dtype=np.float32)
     scores[res.ids] = res.scores
