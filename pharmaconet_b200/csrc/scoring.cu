@@ -106,10 +106,14 @@ struct SmemModel {
   uint8_t* cmask;         // [km]
 };
 
-__host__ __device__ inline size_t smem_model_bytes(int nm, int km, int n_cluster_nodes) {
+// Large models (TG = tables in global memory): the edge table (built once per launch in the workspace) and the
+// cluster-pair tables stay in HBM / L2 / L1; only the small per-node and per-cluster arrays are pinned.
+__host__ __device__ inline size_t smem_model_bytes(int nm, int km, int n_cluster_nodes, bool tables_global) {
   size_t o = 0;
-  o += (size_t)nm * nm * 16;
-  o += (size_t)km * km * 4 * 2;
+  if (!tables_global) {
+    o += (size_t)nm * nm * 16;
+    o += (size_t)km * km * 4 * 2;
+  }
   o += (size_t)nm * 4;
   o += align_up((size_t)(km + 1) * 2, 4);
   o += align_up((size_t)n_cluster_nodes, 4);
@@ -117,6 +121,7 @@ __host__ __device__ inline size_t smem_model_bytes(int nm, int km, int n_cluster
   o += align_up((size_t)km, 4);
   return align_up(o, 16);
 }
+constexpr size_t kSmemTablesMax = 100 * 1024;  // above this the model tables are read from global memory
 
 // Per-warp shared memory of the DFS: the per-depth conformer totals and the candidate-mask stack of the common case
 // (the mask stack is triangular: depth s only keeps the entries of levels >= s). Ligands that need more depth or more
@@ -148,6 +153,7 @@ struct KernelArgs {
   int n_cluster_nodes;
   int conf_stride;  // floats per ligand in out_conf (32 * W)
   WarpLayout ly;    // computed once on the host: the kernel reads the offsets from the constant bank
+  const float4* edge_g;  // large models: the edge table in the workspace (build_edge_table_kernel)
 };
 
 __device__ __forceinline__ float ld_coord(const float* xyz, int stride, int node, int axis, int lane, bool on) {
@@ -264,7 +270,25 @@ __device__ __forceinline__ void pair_term(const SmemModel& sm, const uint8_t* __
 constexpr int block_threads(int W) { return W == 1 ? PM_BLOCK_THREADS : 256; }
 constexpr int min_blocks(int W) { return W == 1 ? PM_MIN_BLOCKS : 2; }
 
-template <int W>
+// float4 {mu, 1/sigma, w_b/sigma, w_a*w_b/sigma} of edge (a, b): the same arithmetic as the reference's fp32 inputs
+__device__ __forceinline__ float4 edge_entry(const PmModel& gm, const float* w, int i, int nm) {
+  const int a = i / nm, b = i % nm;
+  const float r = __fdiv_rn(1.0f, gm.edge_sigma[i]);
+  const float wr = __fmul_rn(w[gm.node_type[b]], r);
+  return make_float4(gm.edge_mu[i], r, wr, __fmul_rn(w[gm.node_type[a]], wr));
+}
+
+struct EdgeTableArgs {
+  PmModel model;
+  float w[PMNET_NUM_TYPES];
+  float4* out;
+};
+__global__ void build_edge_table_kernel(const EdgeTableArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.model.n_nodes * a.model.n_nodes) a.out[i] = edge_entry(a.model, a.w, i, a.model.n_nodes);
+}
+
+template <int W, bool TG>
 __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_kernel(const KernelArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int CW = 32 * W;  // conformer slots per row
@@ -280,27 +304,30 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
   sm.km = KM;
   {
     unsigned char* p = smem_raw;
-    sm.edge = (float4*)p;            p += (size_t)NM * NM * 16;
-    sm.cdist = (float*)p;            p += (size_t)KM * KM * 4;
-    sm.csize = (float*)p;            p += (size_t)KM * KM * 4;
+    if (TG) {
+      sm.edge = const_cast<float4*>(args.edge_g);
+      sm.cdist = const_cast<float*>(gm.cluster_dist);
+      sm.csize = const_cast<float*>(gm.cluster_size_sum);
+    } else {
+      sm.edge = (float4*)p;          p += (size_t)NM * NM * 16;
+      sm.cdist = (float*)p;          p += (size_t)KM * KM * 4;
+      sm.csize = (float*)p;          p += (size_t)KM * KM * 4;
+    }
     sm.wnode = (float*)p;            p += (size_t)NM * 4;
     sm.cnode_off = (uint16_t*)p;     p += align_up((size_t)(KM + 1) * 2, 4);
     sm.cnodes = (uint8_t*)p;         p += align_up((size_t)args.n_cluster_nodes, 4);
     sm.ntype = (uint8_t*)p;          p += align_up((size_t)NM, 4);
     sm.cmask = (uint8_t*)p;          p += align_up((size_t)KM, 4);
   }
-  WarpSmem<W>* ws_all = (WarpSmem<W>*)(smem_raw + smem_model_bytes(NM, KM, args.n_cluster_nodes));
+  WarpSmem<W>* ws_all = (WarpSmem<W>*)(smem_raw + smem_model_bytes(NM, KM, args.n_cluster_nodes, TG));
   WarpSmem<W>& ws = ws_all[warp_in_block];
 
-  for (int i = threadIdx.x; i < NM * NM; i += blockDim.x) {
-    const int a = i / NM, b = i % NM;
-    const float r = __fdiv_rn(1.0f, gm.edge_sigma[i]);
-    const float wr = __fmul_rn(args.w[gm.node_type[b]], r);
-    sm.edge[i] = make_float4(gm.edge_mu[i], r, wr, __fmul_rn(args.w[gm.node_type[a]], wr));
-  }
-  for (int i = threadIdx.x; i < KM * KM; i += blockDim.x) {
-    sm.cdist[i] = gm.cluster_dist[i];
-    sm.csize[i] = gm.cluster_size_sum[i];
+  if (!TG) {
+    for (int i = threadIdx.x; i < NM * NM; i += blockDim.x) sm.edge[i] = edge_entry(gm, args.w, i, NM);
+    for (int i = threadIdx.x; i < KM * KM; i += blockDim.x) {
+      sm.cdist[i] = gm.cluster_dist[i];
+      sm.csize[i] = gm.cluster_size_sum[i];
+    }
   }
   for (int i = threadIdx.x; i < NM; i += blockDim.x) {
     sm.ntype[i] = gm.node_type[i];
@@ -1024,11 +1051,12 @@ int pmnet_abi_version(void) { return PMNET_ABI_VERSION; }
 const char* pmnet_last_error_string(void) { return g_err; }
 
 size_t pmnet_score_workspace_bytes(int32_t n_model_nodes, int32_t n_model_clusters, const PmScoreConfig* cfg) {
-  (void)n_model_nodes;
   PmScoreConfig c;
   resolve_cfg(cfg, &c, cfg == nullptr || cfg->blocks <= 0);
   const WarpLayout L = make_layout(n_model_clusters, c.scratch_rows, conf_words(c.max_conformers));
-  return kHeaderBytes + (size_t)c.blocks * c.warps_per_block * L.bytes;
+  // + room for the edge table of a large model (used when the tables do not fit in shared memory)
+  const size_t edge = align_up((size_t)(n_model_nodes > 0 ? n_model_nodes : 0) * (size_t)(n_model_nodes > 0 ? n_model_nodes : 0) * 16, 256);
+  return kHeaderBytes + (size_t)c.blocks * c.warps_per_block * L.bytes + edge;
 }
 
 int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const float* weights, float* out_scores,
@@ -1084,25 +1112,42 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
   const int W = conf_words(c.max_conformers);
   a.conf_stride = 32 * W;
   const size_t wsm = W == 1 ? sizeof(WarpSmem<1>) : (W == 2 ? sizeof(WarpSmem<2>) : sizeof(WarpSmem<4>));
-  const size_t smem = smem_model_bytes(model->n_nodes, model->n_clusters, n_cluster_nodes) + (size_t)c.warps_per_block * wsm;
+  // model tables: pinned in shared memory when they fit next to the per-warp DFS stacks, else read from global memory
+  const bool tg = smem_model_bytes(model->n_nodes, model->n_clusters, n_cluster_nodes, false) > kSmemTablesMax;
+  const size_t smem =
+      smem_model_bytes(model->n_nodes, model->n_clusters, n_cluster_nodes, tg) + (size_t)c.warps_per_block * wsm;
   if (smem > 200 * 1024) {
-    set_err("pmnet_score_batch: model tables do not fit in shared memory");
+    set_err("pmnet_score_batch: per-node / per-cluster model arrays do not fit in shared memory");
     return PMNET_ELIMIT;
   }
-  const void* fn = W == 1 ? (const void*)pmnet_score_kernel<1>
-                          : (W == 2 ? (const void*)pmnet_score_kernel<2> : (const void*)pmnet_score_kernel<4>);
+  a.edge_g = nullptr;
+  if (tg) {
+    // the edge table sits behind the per-warp scratch (pmnet_score_workspace_bytes reserves it)
+    const size_t off = kHeaderBytes + (size_t)c.blocks * c.warps_per_block * a.ly.bytes;
+    EdgeTableArgs ea;
+    ea.model = *model;
+    for (int i = 0; i < PMNET_NUM_TYPES; ++i) ea.w[i] = weights[i];
+    ea.out = (float4*)((unsigned char*)workspace + off);
+    a.edge_g = ea.out;
+    const int n2 = model->n_nodes * model->n_nodes;
+    build_edge_table_kernel<<<(n2 + 255) / 256, 256, 0, stream>>>(ea);
+  }
+  const void* fn;
+  if (W == 1) fn = tg ? (const void*)pmnet_score_kernel<1, true> : (const void*)pmnet_score_kernel<1, false>;
+  else if (W == 2) fn = tg ? (const void*)pmnet_score_kernel<2, true> : (const void*)pmnet_score_kernel<2, false>;
+  else fn = tg ? (const void*)pmnet_score_kernel<4, true> : (const void*)pmnet_score_kernel<4, false>;
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) e = cudaMemsetAsync(workspace, 0, kHeaderBytes, stream);
   if (e != cudaSuccess) {
     set_err(cudaGetErrorString(e));
     return PMNET_ECUDA;
   }
-  if (W == 1)
-    pmnet_score_kernel<1><<<c.blocks, c.warps_per_block * 32, smem, stream>>>(a);
-  else if (W == 2)
-    pmnet_score_kernel<2><<<c.blocks, c.warps_per_block * 32, smem, stream>>>(a);
-  else
-    pmnet_score_kernel<4><<<c.blocks, c.warps_per_block * 32, smem, stream>>>(a);
+  void* kargs[] = {(void*)&a};
+  e = cudaLaunchKernel(fn, dim3(c.blocks), dim3(c.warps_per_block * 32), kargs, smem, stream);
+  if (e != cudaSuccess) {
+    set_err(cudaGetErrorString(e));
+    return PMNET_ECUDA;
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_err(cudaGetErrorString(e));

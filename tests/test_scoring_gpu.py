@@ -326,3 +326,27 @@ def test_screening_cli_on_sdf_directory(tmp_path):
     assert any(r > 0 for r in ref)
     for f, r in zip(files, ref):
         assert abs(got[f] - r) <= REL_TOL * max(abs(r), 1e-12), (f, got[f], r)
+
+
+def test_large_model_tables_in_global_memory():
+    """A model whose edge / cluster tables (182 KB) do not fit in shared memory next to the DFS stacks: the kernel
+    reads them from global memory instead (103 nodes, 45 overlapping clusters, ~90 k tree nodes per ligand)."""
+    from pharmaconet_b200.packing import PackedModel
+    from pharmaconet_b200.pharmacophore_model import PharmacophoreModel
+
+    m = PharmacophoreModel.create("", (0.0, 0.0, 0.0), synthetic.make_hotspot_infos(seed=21, n_hotspots=130))
+    pm = PackedModel.from_model(m)
+    assert pm.num_nodes**2 * 16 + pm.num_clusters**2 * 8 > 100 * 1024
+    batch = LigandBatch.from_typed(synthetic.make_ligands(64, 8, seed=3))
+    out = _run(pm, batch, None)
+    ref = orc.score(pm, batch)
+    assert np.array_equal(out["status"], ref["status"])
+    assert rel_err(out["scores"], ref["scores"]).max() <= REL_TOL
+    assert np.array_equal(out["stats"][:, 0], ref["stats"][:, 0].astype(np.uint32))  # tree nodes
+    assert np.array_equal(out["stats"][:, 1], ref["stats"][:, 1].astype(np.uint32))  # leaves
+    # same answer through the screening driver (per-model order, two streams)
+    from pharmaconet_b200 import screening
+
+    db = scoring.DeviceLigandBatch.from_host(batch, "cuda:0")
+    res = screening.screen_models([pm, load_case("syn0_c8")["model"]], db, host_lib=batch, k=16, keep_scores=True)
+    assert rel_err(res[0].scores.cpu().numpy(), ref["scores"]).max() <= REL_TOL
