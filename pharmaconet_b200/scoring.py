@@ -113,6 +113,30 @@ def big_config(model) -> ScoreConfig:
     return ScoreConfig(warps_per_block=4, blocks=16, scratch_rows=rows)
 
 
+def mid_config(model) -> ScoreConfig:
+    """Four times the default pair-table scratch on half the warps: the first retry for ligands that overflowed the
+    default scratch (wide models push many ligands past 8192 pair rows; `big_config` alone would serialise them on
+    64 warps)."""
+    return ScoreConfig(warps_per_block=16, blocks=0, scratch_rows=32768)
+
+
+def rescore_overflowed(model: "DeviceModel", sub: LigandBatch, weights=None, with_stats: bool = False) -> dict:
+    """Score ligands whose pair table overflowed the default per-warp scratch: `mid_config` first, `big_config` for
+    what still does not fit. `sub` is a host batch of just those ligands; returns device tensors like score_batch."""
+    dev_sub = DeviceLigandBatch.from_host(sub, model.device)
+    out = score_batch(model, dev_sub, weights, mid_config(model), with_stats=with_stats)
+    still = torch.nonzero(out["status"] == _abi.LIG_OVERFLOW).flatten()
+    if still.numel():
+        idx = still.cpu().numpy()
+        o2 = score_batch(
+            model, DeviceLigandBatch.from_host(sub.select(idx), model.device), weights, big_config(model),
+            with_stats=with_stats,
+        )  # fmt: skip
+        for k in out:
+            out[k][still] = o2[k]
+    return out
+
+
 _workspaces: dict[tuple, torch.Tensor] = {}
 
 
@@ -199,10 +223,7 @@ def score_library(
     stats = out["stats"].cpu().numpy().view(np.uint32) if with_stats else None
     over = np.nonzero(status == _abi.LIG_OVERFLOW)[0]
     if len(over):
-        sub = host_batch.select(over)
-        o2 = score_batch(
-            model, DeviceLigandBatch.from_host(sub, model.device), weights, big_config(model), with_stats=with_stats
-        )
+        o2 = rescore_overflowed(model, host_batch.select(over), weights, with_stats=with_stats)
         scores[over] = o2["scores"].cpu().numpy()
         status[over] = o2["status"].cpu().numpy()
         if with_stats:

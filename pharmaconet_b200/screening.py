@@ -20,7 +20,7 @@ import torch
 from . import _abi
 from .packing import LigandBatch, PackedModel
 from .scoring import (
-    DeviceLigandBatch, DeviceModel, ScoreConfig, big_config, cost_order, order_workspace_bytes as _lib_order_bytes,
+    DeviceLigandBatch, DeviceModel, ScoreConfig, cost_order, order_workspace_bytes as _lib_order_bytes, rescore_overflowed,
     score_batch, topk, workspace_bytes,
 )  # fmt: skip
 
@@ -277,7 +277,7 @@ class Screener:
         over = np.nonzero(st == _abi.LIG_OVERFLOW)[0]
         if len(over):
             sub = lib.select(ids[over])
-            o2 = score_batch(self.model, DeviceLigandBatch.from_host(sub, dev), self.weights, big_config(self.model))
+            o2 = rescore_overflowed(self.model, sub, self.weights)
             scores[torch.from_numpy(over).to(dev)] = o2["scores"]
             launches += 1
             over_ids = torch.from_numpy(ids[over]).to(dev)
@@ -356,7 +356,7 @@ def screen_models(
         launches = 4
         if n_over and host_lib is not None:
             sub = host_lib.select(over.cpu().numpy())
-            o2 = score_batch(dm, DeviceLigandBatch.from_host(sub, dev), weights, big_config(dm))
+            o2 = rescore_overflowed(dm, sub, weights)
             o["scores"][over] = o2["scores"]
             ks, ki = topk(o["scores"], k, id_base)
             launches += 3

@@ -22,9 +22,14 @@ ap.add_argument("--warps", type=int, default=0)
 ap.add_argument("--blocks", type=int, default=0)
 ap.add_argument("--rows", type=int, default=0)
 ap.add_argument("--tiny", action="store_true")
+ap.add_argument("--hotspots", type=int, default=0, help="build a synthetic model with this many hotspots instead of syn0")
 a = ap.parse_args()
 
-model = PharmacophoreModel.load(os.path.join(ROOT, "tests", "golden", "model_syn0.pm"))
+if a.hotspots:
+    model = PharmacophoreModel.create("", (0.0, 0.0, 0.0), synthetic.make_hotspot_infos(seed=21, n_hotspots=a.hotspots))
+    print(f"synthetic model: {len(model.nodes)} nodes, {len(model.node_clusters)} clusters", flush=True)
+else:
+    model = PharmacophoreModel.load(os.path.join(ROOT, "tests", "golden", "model_syn0.pm"))
 dm = scoring.DeviceModel(PackedModel.from_model(model), "cuda:0")
 t = time.time()
 base = LigandBatch.from_typed(synthetic.make_ligands(a.unique, a.conf, seed=1))
