@@ -36,9 +36,17 @@ _GROUPED = (
 _SINGLE = (("HBond", "HBond"), ("Hydrophobic", "Hydrophobic"), ("Halogen", "XBond"))
 
 
-def connected_components(mask: np.ndarray):
-    """Yield (voxels [n,3] int, values [n] float) of the 26-connected components of `mask > 0`."""
-    xs, ys, zs = np.where(mask > 0.0)
+def connected_components(mask):
+    """Yield (voxels [n,3] int, values [n] float) of the 26-connected components of `mask > 0`.
+
+    mask: the dense [D,H,W] map, or its non-zero voxels as a pair (coords int [n,3] in C order, values [n]) - what
+    `PharmacoNet.create_models` brings back from the device instead of the dense maps."""
+    if isinstance(mask, tuple):
+        coords, vals = mask
+        xs, ys, zs = coords[:, 0], coords[:, 1], coords[:, 2]
+        mask = {(int(x), int(y), int(z)): v for x, y, z, v in zip(xs, ys, zs, vals)}
+    else:
+        xs, ys, zs = np.where(mask > 0.0)
     todo = {(int(x), int(y), int(z)) for x, y, z in zip(xs, ys, zs)}
     while todo:
         seed = todo.pop()
@@ -74,7 +82,7 @@ def build_model_state(pdbblock: str, center, hotspot_infos: list[dict], resoluti
     radius: list[float] = []
     for info in hotspot_infos:
         hp = tuple(np.asarray(info["hotspot_position"]).tolist())
-        for vox, val in connected_components(info["point_map"]):
+        for vox, val in connected_components(info["point_map_sparse"] if "point_map_sparse" in info else info["point_map"]):
             if len(vox) < MIN_VOXELS:
                 continue
             c = np.average(vox, axis=0, weights=val)

@@ -239,7 +239,11 @@ class PharmacoNet:
         pdbblocks = pdbblocks or [""] * n
         models = []
         for lo in range(0, n, chunk):
-            infos = self.create_density_maps_batch(protein_data_list[lo : lo + chunk])
+            # only the non-zero voxels of the maps come back from the device (KBs instead of 1 MB per hotspot)
+            infos = [
+                self._density_maps_of(r, sparse=True)
+                for r in self._features_and_hotspots_batch(protein_data_list[lo : lo + chunk], nchw=False)
+            ]
             for k, info in enumerate(infos):
                 models.append(PharmacophoreModel.create(pdbblocks[lo + k], tuple(float(c) for c in centers[lo + k]), info))
         return models
@@ -250,7 +254,9 @@ class PharmacoNet:
         # the maps stay in the kernels' layout
         return [self._density_maps_of(r) for r in self._features_and_hotspots_batch(protein_data_list, nchw=False)]
 
-    def _density_maps_of(self, r) -> list[HotspotInfo]:
+    def _density_maps_of(self, r, sparse: bool = False) -> list[HotspotInfo]:
+        """sparse: give `point_map_sparse` = (voxel coordinates int32 [n,3] in C order, values fp32 [n]) instead of
+        the dense `point_map` - the form `PharmacophoreModel.create` consumes without a 64^3 scan per hotspot."""
         hotspots, feats = r["hotspots"], r["feats"]
         logits = []
         if hotspots.shape[0] > 0:
@@ -262,21 +268,33 @@ class PharmacoNet:
         if logits:
             maps = cnn.density_post(torch.cat(logits, 0), hotspots, r["mask"], r["narrow"][0], self.box_threshold)
             alive = (maps.reshape(maps.shape[0], -1) >= 1e-6).any(dim=1).cpu().tolist()  # module.py:292-293
-            maps = maps.cpu().numpy()
-            for k, (hotspot, score, pos) in enumerate(zip(hotspots, r["rel_scores"], r["positions"], strict=True)):
+            if sparse:
+                nz = torch.nonzero(maps > 0)  # [n, 4] = (hotspot, x, y, z), lexicographic = np.where order per map
+                vals = maps[nz[:, 0], nz[:, 1], nz[:, 2], nz[:, 3]].cpu().numpy()
+                counts = torch.bincount(nz[:, 0], minlength=maps.shape[0]).cpu().numpy()
+                coords = nz[:, 1:].to(torch.int32).cpu().numpy()
+                ends = np.cumsum(counts)
+            else:
+                maps = maps.cpu().numpy()
+            positions = r["positions"].cpu().numpy()
+            types = hotspots[:, 3].cpu().tolist()
+            for k, score in enumerate(r["rel_scores"]):
                 if not alive[k]:
                     continue
-                name = INTERACTION_LIST[int(hotspot[3])]
-                infos.append(
-                    dict(
-                        nci_type=name,
-                        hotspot_type=INTERACTION_TO_HOTSPOT[name],
-                        hotspot_position=pos.cpu().numpy(),
-                        hotspot_score=score,
-                        point_type=INTERACTION_TO_PHARMACOPHORE[name],
-                        point_map=maps[k],
-                    )
+                name = INTERACTION_LIST[int(types[k])]
+                info = dict(
+                    nci_type=name,
+                    hotspot_type=INTERACTION_TO_HOTSPOT[name],
+                    hotspot_position=positions[k],
+                    hotspot_score=score,
+                    point_type=INTERACTION_TO_PHARMACOPHORE[name],
                 )
+                if sparse:
+                    lo = int(ends[k] - counts[k])
+                    info["point_map_sparse"] = (coords[lo : int(ends[k])], vals[lo : int(ends[k])])
+                else:
+                    info["point_map"] = maps[k]
+                infos.append(info)
         self.print_log("debug", f"Protein-based Pharmacophore Modeling finish (Total {len(infos)} protein hotspots are detected)")
         return infos
 

@@ -58,3 +58,19 @@ def test_small_components_are_dropped():
     model = PharmacophoreModel.create("", (0.0, 0.0, 0.0), [info])
     assert len(model.nodes) == 1 and len(model.node_clusters) == 1
     assert abs(model.nodes[0].radius - (27 / (4 * np.pi / 3)) ** (1 / 3) * 0.5) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["syn0", "loose"])
+def test_sparse_maps_give_the_same_model_state(name):
+    """`point_map_sparse` (non-zero voxels in C order, what create_models copies back from the device) == dense maps."""
+    infos = synthetic.make_hotspot_infos(**MODELS[name])
+    dense = PharmacophoreModel.create("", (1.0, -2.0, 0.5), infos).__getstate__()
+    sparse_infos = []
+    for info in infos:
+        m = info["point_map"]
+        coords = np.argwhere(m > 0).astype(np.int32)
+        d = {k: v for k, v in info.items() if k != "point_map"}
+        d["point_map_sparse"] = (coords, m[coords[:, 0], coords[:, 1], coords[:, 2]])
+        sparse_infos.append(d)
+    sparse = PharmacophoreModel.create("", (1.0, -2.0, 0.5), sparse_infos).__getstate__()
+    assert pickle.dumps(dense) == pickle.dumps(sparse)

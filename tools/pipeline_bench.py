@@ -43,18 +43,29 @@ def sync():
 
 net.create_models(data[:1])  # warm-up (allocations, cuBLAS handles)
 sync()
-t0 = time.perf_counter()
-maps = net.create_density_maps_batch(data)
-sync()
-t1 = time.perf_counter()
 from pharmaconet_b200.pharmacophore_model import PharmacophoreModel  # noqa: E402
 
-models = [PharmacophoreModel.create("", (0.0, 0.0, 0.0), m) for m in maps]
+t0 = time.perf_counter()
+rs = []
+for lo in range(0, a.pockets, a.chunk):
+    rs += net._features_and_hotspots_batch(data[lo : lo + a.chunk], nchw=False)
+sync()
+t1 = time.perf_counter()
+maps = [net._density_maps_of(r, sparse=True) for r in rs]
+sync()
 t2 = time.perf_counter()
+models = [PharmacophoreModel.create("", (0.0, 0.0, 0.0), m) for m in maps]
+t3 = time.perf_counter()
 nh = [len(m) for m in maps]
-print(f"{a.pockets} pockets: density maps {1e3 * (t1 - t0) / a.pockets:.1f} ms/pocket (GPU forward + mask head + post, "
-      f"{np.mean(nh):.0f} hotspots/pocket), model graphs {1e3 * (t2 - t1) / a.pockets:.1f} ms/pocket (host), "
-      f"{np.mean([len(m.nodes) for m in models]):.0f} nodes / {np.mean([len(m.node_clusters) for m in models]):.0f} clusters")
+print(f"{a.pockets} pockets, per pocket: features + token / cavity heads + hotspot filter {1e3 * (t1 - t0) / a.pockets:.1f} ms "
+      f"(incl. H2D of the 33 x 64^3 grids), mask head + density post + sparse D2H {1e3 * (t2 - t1) / a.pockets:.1f} ms "
+      f"({np.mean(nh):.0f} hotspots), model graph on the host {1e3 * (t3 - t2) / a.pockets:.1f} ms "
+      f"({np.mean([len(m.nodes) for m in models]):.0f} nodes / {np.mean([len(m.node_clusters) for m in models]):.0f} clusters)")
+sync()
+t0 = time.perf_counter()
+net.create_models(data, chunk=a.chunk)
+sync()
+print(f"create_models end to end: {1e3 * (time.perf_counter() - t0) / a.pockets:.1f} ms/pocket")
 models = [m for m in models if len(m.nodes) > 0]
 lib = synthetic.make_library_device(a.ligands, a.conformers, 1, dev, 4096)
 screening.screen_models(models[:1], lib, k=100)  # warm-up
