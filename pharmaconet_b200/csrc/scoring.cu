@@ -6,18 +6,21 @@
 //   ClusterMatchTree.dfs_run        src/pmnet/scoring/tree.py:55-104
 //   GraphMatcher._run_average       src/pmnet/scoring/graph_match.py:103-109
 //
-// Design:
-//  * persistent grid, warps pull ligands from a global counter (DFS cost varies by 100x between ligands);
-//  * the pharmacophore model (edge table as float4 {mu, 1/sigma, w_b/sigma, -}, cluster tables) is pinned in shared
-//    memory once per block; ligand coordinates stream from HBM as 128 B rows (lane = conformer);
+// Design (DESIGN.md sections 3-4):
+//  * persistent grid (one 32-warp CTA per SM for up to 32 conformers), warps pull ligands from a global counter,
+//    optionally through a longest-first permutation (pmnet_cost_order): DFS cost varies by 100x between ligands;
+//  * the pharmacophore model (edge table as float4 {mu, 1/sigma, w_b/sigma, w_a w_b/sigma}, cluster tables) is pinned
+//    in shared memory once per block (read from global memory instead when it exceeds 100 KB); ligand coordinates
+//    stream from HBM as 128 B rows (lane = conformer);
 //  * phase 1 evaluates every (ligand cluster i, model cluster k) x (j, l) pair score once. Only what the tree
 //    needs is kept: a 32-bit conformer-validity word V per pair (pair score > 0) and, for pairs with V != 0, one
 //    128 B row of fp32 scores in a per-warp scratch pool;
 //  * phase 2 is the DFS with an explicit stack. Candidate sets are bit masks: a child's masks are
 //    parent_mask & alive & V, updated 32 candidates at a time (lane = candidate), the "any conformer left" tests
-//    are word != 0, per-depth control state lives in lane-indexed registers (lane d = depth d);
-//    per-conformer totals are only formed for the node being created: total' = total + self + sum of pair rows
-//    with the matched ancestors.
+//    are word != 0, per-depth control state lives in lane-indexed registers (lane d = depth d); the (triangular) mask
+//    stack and the per-depth totals sit in shared memory; per-conformer totals are only formed for the node being
+//    created: total' = total + self + sum of pair rows with the matched ancestors; all leaf children of a node are
+//    evaluated in one pass.
 // The discrete decisions (prefilter, sigma^2 < 4, fail counts, score > 0, the < 5 rule) use the same fp32
 // operations as the reference (no FMA contraction on those paths), so they agree bit for bit; the accumulated
 // scores are fp32 here (fp64 in the reference) and agree to ~1e-6 relative.
