@@ -289,7 +289,8 @@ def main():
         numa_cpus = bind_to_gpu(local_rank)
     if world > 1:
         # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) out of it
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        # (it can also come from /etc/nccl.conf, which never overrides an environment variable)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
