@@ -129,8 +129,14 @@ constexpr size_t kSmemTablesMax = 100 * 1024;  // above this the model tables ar
 // Per-warp shared memory of the DFS: the per-depth conformer totals and the candidate-mask stack of the common case
 // (the mask stack is triangular: depth s only keeps the entries of levels >= s). Ligands that need more depth or more
 // mask words use the same layout in the global workspace instead.
-constexpr int kSmemTotFloats = 12 * 32;  // 12 depths of 32 conformers (6 of 64, 3 of 128)
-constexpr int kSmemMaskWords = 256;
+#ifndef PM_SMEM_TOT_SLOTS
+#define PM_SMEM_TOT_SLOTS 12
+#endif
+#ifndef PM_SMEM_MASK_WORDS
+#define PM_SMEM_MASK_WORDS 256
+#endif
+constexpr int kSmemTotFloats = PM_SMEM_TOT_SLOTS * 32;  // 12 depths of 32 conformers (6 of 64, 3 of 128)
+constexpr int kSmemMaskWords = PM_SMEM_MASK_WORDS;
 template <int W>
 struct WarpSmem {
   float tot[kSmemTotFloats];
@@ -913,6 +919,22 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
                   for (int u = 0; u < 4; ++u)
 #pragma unroll
                     for (int w = 0; w < W; ++w) acc[w] += vv[u][w];
+                }
+                {
+                  // no candidate left at any later level: the child's subtree is the chain of None nodes down to the
+                  // None leaf (tree.py:98 with nchild == 0 at every level) - account for it without walking it
+                  unsigned any0 = 0;
+#pragma unroll
+                  for (int w = 0; w < W; ++w) any0 |= pmv[w] & alive2[w] & vtv[w];
+                  if (T - end <= 32 && !__any_sync(kFull, any0 != 0u)) {
+                    st_nodes += L - d - 1;
+                    ++st_leaves;
+#pragma unroll
+                    for (int w = 0; w < W; ++w)
+                      if ((alive2[w] >> lane) & 1u) best[w] = fmaxf(best[w], t[w] + acc[w]);
+                    if (lane == d) st_maxm = max(st_maxm, 1);
+                    continue;
+                  }
                 }
                 const int nmatch = __shfl_sync(kFull, st_nmatch, d) + 1;
                 // the child's candidate masks: parent mask & conformers alive in the child & pair validity.
