@@ -937,6 +937,76 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
                   }
                 }
                 const int nmatch = __shfl_sync(kFull, st_nmatch, d) + 1;
+                if (d + 2 == L && T - end <= 32) {
+                  // ---- the child's own children are leaves and their masks are in registers (lane = entry of the last
+                  // level): evaluate them here, exactly like the leaf pass above with the child as one more ancestor,
+                  // instead of pushing the child, storing its masks / totals and coming back for them
+                  unsigned nmw[W];
+                  unsigned anyw = 0;
+                  float tt[W];
+#pragma unroll
+                  for (int w = 0; w < W; ++w) {
+                    nmw[w] = pmv[w] & alive2[w] & vtv[w];
+                    anyw |= nmw[w];
+                    tt[w] = t[w] + acc[w];
+                  }
+                  unsigned bal = __ballot_sync(kFull, anyw != 0u);  // not empty: the dead-end case was taken above
+                  const bool is_anc2 = is_anc || lane == d + 1;
+                  const int pb2 = (lane == d + 1) ? pbc : st_pbase;
+                  int nleaf = 0;
+                  int nf = end + __ffs(bal) - 1;
+                  int myrow_n = is_anc2 ? prow[pb2 + nf] : -1;
+                  int sr_n = srow[nf];
+                  while (bal) {
+                    const int src = __ffs(bal) - 1;
+                    bal &= bal - 1;
+                    const int myrow2 = myrow_n, sr2 = sr_n;
+                    if (bal) {
+                      nf = end + __ffs(bal) - 1;
+                      myrow_n = is_anc2 ? prow[pb2 + nf] : -1;
+                      sr_n = srow[nf];
+                    }
+                    float tl[W], self[W];
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                      self[w] = (sr2 >= 0) ? rows_l[(sr2 * W + w) * 32] : 0.0f;
+                      tl[w] = 0.0f;
+                    }
+                    for (int d0 = 1; d0 <= d + 1; d0 += 4) {
+                      int rr[4];
+#pragma unroll
+                      for (int u = 0; u < 4; ++u) rr[u] = __shfl_sync(kFull, myrow2, d0 + u);
+                      float vv[4][W];
+#pragma unroll
+                      for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int w = 0; w < W; ++w)
+                          vv[u][w] = (rr[u] >= 0) ? rows_l[(rr[u] * W + w) * 32] : 0.0f;
+#pragma unroll
+                      for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int w = 0; w < W; ++w) tl[w] += vv[u][w];
+                    }
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                      const unsigned al = __shfl_sync(kFull, nmw[w], src);
+                      if ((al >> lane) & 1u) best[w] = fmaxf(best[w], (tt[w] + self[w]) + tl[w]);
+                    }
+                    ++nleaf;
+                  }
+                  st_nodes += nleaf;
+                  st_leaves += nleaf;
+                  if (nmatch + 1 < PMNET_MIN_MATCHES) {
+                    // the child's None leaf (tree.py:98: too few matches on the path)
+                    ++st_nodes;
+                    ++st_leaves;
+#pragma unroll
+                    for (int w = 0; w < W; ++w)
+                      if ((alive2[w] >> lane) & 1u) best[w] = fmaxf(best[w], tt[w]);
+                  }
+                  if (lane == d) st_maxm = max(st_maxm, 2);  // the child returns 1 (a matched leaf) + 1 (itself)
+                  continue;
+                }
                 // the child's candidate masks: parent mask & conformers alive in the child & pair validity.
                 // (depth d + 1's slot was last read by other lanes while the previous child's subtree was walked)
                 __syncwarp();
