@@ -94,3 +94,34 @@ def test_charges_and_conformers(tmp_path):
     assert ("Cation", 0, 0) in [tuple(p) for p in lig.pharmacophores]
     assert not any(p[0] == "HBond_acceptor" for p in lig.pharmacophores)  # N+ with four bonds
     assert typed_ligand_from_file(str(path), num_conformers=2, perception="builtin").num_conformers == 2
+
+
+def test_pack_library_tool_roundtrip(tmp_path):
+    """tools/pack_library.py: directory of .sdf files -> packed .npz that load_library reads back identically."""
+    import os
+    import subprocess
+    import sys
+
+    from pharmaconet_b200.packing import LigandBatch, load_library
+
+    lib = tmp_path / "lib"
+    lib.mkdir()
+    atoms, bonds = ring(6, "CCCCCC", [2, 1, 2, 1, 2, 1], [("O", 2.8, 0.0, 0.0), ("H", 3.4, 0.7, 0.0)], [(1, 7, 1), (7, 8, 1)])
+    (lib / "b_phenol.sdf").write_text(molblock(atoms, bonds) * 3)
+    (lib / "a_amine.sdf").write_text(
+        molblock([("N", 0, 0, 0), ("C", 1.4, 0, 0), ("C", -0.7, 1.2, 0), ("C", -0.7, -1.2, 0)], [(1, 2, 1), (1, 3, 1), (1, 4, 1)]) * 2
+    )
+    (lib / "c_broken.sdf").write_text("not a molfile\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "lib.npz"
+    r = subprocess.run(
+        [sys.executable, os.path.join(root, "tools", "pack_library.py"), "-d", str(lib), "-o", str(out), "--perception", "builtin"],
+        check=True, capture_output=True, text=True, timeout=120,
+    )  # fmt: skip
+    assert "2 ligands, 5 conformers" in r.stdout and "c_broken.sdf" in r.stderr
+    batch, names = load_library(out)
+    assert [os.path.basename(n) for n in names] == ["a_amine.sdf", "b_phenol.sdf"]
+    assert list(batch.n_conf) == [2, 3]
+    ref = LigandBatch.from_typed([typed_ligand_from_file(str(lib / n), perception="builtin") for n in ("a_amine.sdf", "b_phenol.sdf")])
+    for k, v in ref.arrays().items():
+        assert np.array_equal(v, batch.arrays()[k]), k
