@@ -74,3 +74,18 @@ def test_write_csv_matches_reference_format(tmp_path):
     p = tmp_path / "out.csv"
     screening.write_csv(str(p), ["a.sdf", "b.sdf", "c.sdf"], [1.5, 3.0, 1.5])
     assert p.read_text().splitlines() == ["path,score", "b.sdf,3.0", "a.sdf,1.5", "c.sdf,1.5"]
+
+
+def test_numa_binding_is_a_noop_without_nvml():
+    """affinity.bind_to_gpu never raises and leaves the affinity alone when NVML / the GPU is not there (this container)."""
+    import os
+
+    from pharmaconet_b200.affinity import bind_to_gpu
+
+    before = os.sched_getaffinity(0)
+    cpus = bind_to_gpu(0)
+    if cpus is None:
+        assert os.sched_getaffinity(0) == before
+    else:  # a GPU box: bound to a non-empty subset of what was allowed
+        assert set(cpus) <= before and len(cpus) > 0
+        os.sched_setaffinity(0, before)
