@@ -75,3 +75,28 @@ def test_file_entry_points_fail_loudly_without_openbabel():
             lt.typed_ligand_from_file("x.mol2")
         with pytest.raises(ImportError, match="OpenBabel"):
             lt.typed_ligand_from_file("x.sdf", perception="openbabel")
+
+
+def test_rules_match_the_reference_on_real_molecules():
+    """tests/golden/typing_examples.json (oracle/make_golden_typing.py): the UNMODIFIED reference
+    `get_pharmacophore_nodes` (ligand_utils.py:25-88) run on duck-typed atoms answering the OpenBabel queries from the
+    stored tables - 400 molecules of the reference's examples/library.tar + hand-made rare groups. The rules layer
+    must reproduce its pharmacophore list exactly (types, atom keys, centre keys, order)."""
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "typing_examples.json")
+    recs = json.load(open(path))
+    assert len(recs) >= 400
+    seen = set()
+    for r in recs:
+        t = r["table"]
+        table = lt.AtomTable(
+            atomic_nums=t["atomic_nums"], neighbors=t["neighbors"], explicit_degree=t["explicit_degree"],
+            heavy_degree=t["heavy_degree"], hyb=t["hyb"], is_acceptor=t["is_acceptor"], is_donor=t["is_donor"],
+            aromatic_rings=[tuple(x) for x in t["aromatic_rings"]],
+        )  # fmt: skip
+        mine = json.loads(json.dumps([[a, b, c] for a, b, c in lt.type_atoms(table)]))
+        assert mine == r["pharmacophores"], r["name"]
+        seen |= {p[0] for p in mine}
+    assert seen == {"Hydrophobic", "Aromatic", "Cation", "Anion", "HBond_donor", "HBond_acceptor", "Halogen"}
