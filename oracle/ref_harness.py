@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE - import harness for the *real* reference (SeonghwanSeo/PharmacoNet) in the build container.
 
-Only `oracle/make_golden.py` and ad-hoc probes use this module. It reads `/root/reference`, which does not exist
-on the GPU box: nothing under `tests/ -m gpu`, `bench.py` or `__graft_entry__.smoke()` may import it.
+Used by `oracle/make_golden*.py` (build container, `/root/reference`) and by `oracle/ref_pool.py`, the CPU-baseline
+arm of bench.py, which on the GPU box imports the unmodified copy `oracle/_ref/pmnet` made by `oracle/make_ref.py`.
 The product package never imports anything from `oracle/`.
 
 Recipe: SURVEY.md Appendix D. OpenBabel / molvoxel / omegaconf / biopython are absent, so they are stubbed; the
@@ -15,12 +15,16 @@ import os
 import sys
 from unittest.mock import MagicMock
 
-REFERENCE_SRC = os.environ.get("PMNET_REFERENCE_SRC", "/root/reference/src")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# build container: the reference where it lies; GPU box: the unmodified copy made by oracle/make_ref.py (git-ignored)
+REFERENCE_SRC = os.environ.get("PMNET_REFERENCE_SRC") or (
+    "/root/reference/src" if os.path.isdir("/root/reference/src/pmnet") else os.path.join(_HERE, "_ref")
+)
 
 
 def import_reference():
-    if not os.path.isdir(REFERENCE_SRC):
-        raise RuntimeError(f"reference sources not found at {REFERENCE_SRC} (only available in the build container)")
+    if not os.path.isdir(os.path.join(REFERENCE_SRC, "pmnet")):
+        raise RuntimeError(f"reference sources not found at {REFERENCE_SRC} (run oracle/make_ref.py in the build container)")
     os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")  # reference tree is read-only, kernels use cache=True
     for name in ["openbabel", "openbabel.pybel", "molvoxel", "omegaconf", "Bio", "Bio.PDB", "Bio.PDB.PDBIO"]:
         sys.modules.setdefault(name, MagicMock())

@@ -270,11 +270,15 @@ def make_library_device(
     n_templates: int = 4096,
     flex: float = 0.45,
     noise: float = 0.08,
+    keep_atoms: int = 0,
 ):
     """Large synthetic library built on the GPU (benchmarks): `n_templates` topologies from `make_template`, each
     replicated with independently drawn coordinates (same recipe as `make_conformers`, in torch on `device`).
     Ligand i uses template i % n_templates, so any prefix of the library is a representative sample.
-    Returns a `scoring.DeviceLigandBatch`. Data creation only - nothing here is scored or timed."""
+    Returns a `scoring.DeviceLigandBatch`. Data creation only - nothing here is scored or timed.
+    keep_atoms = n (<= n_templates): also keep the ATOM coordinates of the first n ligands and attach them as
+    `batch.typed_prefix` (list of TypedLigand) - the same ligands in the form the reference's own `LigandGraph`
+    consumes (bench.py's reference arm)."""
     import torch
 
     from .ligand import build_topology
@@ -288,6 +292,8 @@ def make_library_device(
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
 
+    keep_atoms = min(int(keep_atoms), T)
+    typed_prefix: list = []
     templates, tops = [], []
     for _ in range(T):
         t = make_template(rng)
@@ -353,6 +359,8 @@ def make_library_device(
         local = torch.einsum("rnij,nj->rni", rot[:, f], torch.as_tensor(t.local_xyz, device=dev))
         pos = centres[:, f][:, :, None, :] + bend[:, :, f, :].permute(0, 2, 1, 3) + local[:, :, None, :]
         pos = pos + noise * torch.randn(pos.shape, generator=gen, device=dev, dtype=torch.float32)  # [r, N, C, 3]
+        if t_i < keep_atoms:  # ligand t_i is replica 0 of template t_i
+            typed_prefix.append(t.typed(np.ascontiguousarray(pos[0].cpu().numpy()), name=f"lib{seed}_{t_i}"))
         A = torch.zeros((nn, N), dtype=torch.float32, device=dev)
         for n_i, ctr in enumerate(top.node_center_atoms):
             A[n_i, list(ctr)] = 1.0 / len(ctr)
@@ -373,4 +381,16 @@ def make_library_device(
     )
     tensors = {k: torch.from_numpy(v).to(dev) for k, v in host.items()}
     tensors["coords"] = coords
-    return DeviceLigandBatch(tensors, n_ligands, n_ligands * C, max_conformers=C)
+    if typed_prefix:
+        # node coordinates of the kept ligands through the host featuriser (ligand.node_positions: the reference's own
+        # fp32 arithmetic, ligand.py:293-301) instead of the einsum above, so that the device library and the
+        # reference's LigandGraph built from `typed_prefix` hold bit-identical node positions
+        from .packing import LigandBatch
+
+        lb = LigandBatch.from_typed(typed_prefix)
+        n_keep = len(typed_prefix)
+        assert np.array_equal(lb.coord_off, coord_off[: n_keep + 1]) and np.array_equal(lb.node_type_mask, masks[: int(node_off[n_keep])])
+        coords[: int(coord_off[n_keep])] = torch.from_numpy(lb.coords).to(dev)
+    batch = DeviceLigandBatch(tensors, n_ligands, n_ligands * C, max_conformers=C)
+    batch.typed_prefix = typed_prefix
+    return batch

@@ -9,8 +9,20 @@ from pharmaconet_b200.packing import LigandBatch, PackedModel
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(
-    os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(f).startswith("cnn_")
+    os.path.basename(f)[:-4]
+    for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
+    if not os.path.basename(f).startswith(("cnn_", "fallback_", "typing_"))
 )  # scoring cases; cnn_*.npz belong to tests/test_cnn_gpu.py
+# scores of the same ligands by the reference's numpy fallback scorer (match_utils.py; oracle/make_golden_fallback.py)
+FALLBACK_CASES = sorted(
+    os.path.basename(f)[len("fallback_") : -4] for f in glob.glob(os.path.join(GOLDEN, "fallback_*.npz"))
+)
+
+
+def load_fallback(name):
+    z = np.load(os.path.join(GOLDEN, f"fallback_{name}.npz"))
+    assert str(z["base_case"]) == name
+    return z["ref_scores"]
 
 
 def load_case(name):

@@ -3,7 +3,7 @@ oracle/make_golden.py with GraphMatcher.run of /root/reference). This is what pi
 
 import numpy as np
 import pytest
-from golden_util import CASES, load_case, rel_err
+from golden_util import CASES, FALLBACK_CASES, load_case, load_fallback, rel_err
 
 import oracle as orc
 
@@ -37,3 +37,15 @@ def test_oracle_subrange():
     full = orc.score(c["model"], c["batch"], c["weights"], threads=2)
     part = orc.score(c["model"], c["batch"], c["weights"], threads=2, begin=10, end=50)
     assert np.array_equal(full["scores"][10:50], part["scores"])
+
+
+@pytest.mark.parametrize("name", FALLBACK_CASES)
+def test_oracle_matches_reference_numpy_fallback(name):
+    """The reference's second scorer (match_utils.py:9-122, all fp32; selected at graph_match.py:12-15 when numba is
+    missing) on the same ligands: same discrete decisions, scores equal up to its fp32 accumulation (observed 3e-8)."""
+    c = load_case(name)
+    fb = load_fallback(name)
+    out = orc.score(c["model"], c["batch"], c["weights"], threads=0)
+    assert rel_err(out["scores"], fb).max() <= 1e-6
+    assert np.array_equal(out["scores"] == 0.0, fb == 0.0)
+    assert rel_err(c["ref"], fb).max() <= 1e-6  # the two reference variants agree with each other

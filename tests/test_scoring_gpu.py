@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 import torch
-from golden_util import CASES, load_case, rel_err, weights_dict
+from golden_util import CASES, FALLBACK_CASES, load_case, load_fallback, rel_err, weights_dict
 
 import oracle as orc
 from pharmaconet_b200 import _abi, scoring, synthetic
@@ -27,6 +27,16 @@ def test_kernel_matches_reference_golden(name):
     assert rel_err(out["scores"], c["ref"]).max() <= REL_TOL
     # exact zeros where the reference returns 0 (no candidates)
     assert np.array_equal(out["scores"] == 0.0, c["ref"] == 0.0)
+
+
+@pytest.mark.parametrize("name", FALLBACK_CASES)
+def test_kernel_matches_reference_numpy_fallback(name):
+    """second reference scorer (match_utils.py, fp32 throughout; graph_match.py:12-15) on the same ligands"""
+    c = load_case(name)
+    fb = load_fallback(name)
+    out = _run(c["model"], c["batch"], c["weights"])
+    assert rel_err(out["scores"], fb).max() <= REL_TOL
+    assert np.array_equal(out["scores"] == 0.0, fb == 0.0)
 
 
 @pytest.mark.parametrize("name", CASES)
