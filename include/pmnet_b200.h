@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PMNET_ABI_VERSION 2
+#define PMNET_ABI_VERSION 3
 
 /* pharmacophore types, bit positions of every type mask (graph_match.py:32-40) */
 enum {
@@ -55,7 +55,9 @@ enum {
   PMNET_LIG_OK = 0,
   PMNET_LIG_EMPTY = 1,    /* no cluster / no candidate: score 0 (graph_match.py:95-99), not an error */
   PMNET_LIG_OVERFLOW = 2, /* per-warp scratch exhausted: score not computed; re-run with a larger scratch */
-  PMNET_LIG_UNSUPPORTED = 3 /* more conformers than PMNET_MAX_CONFORMERS */
+  PMNET_LIG_UNSUPPORTED = 3, /* more conformers than PMNET_MAX_CONFORMERS */
+  PMNET_LIG_DEFERRED = 4     /* internal: left by the specialised kernel for the general kernel that pmnet_score_batch
+                                enqueues behind it in the same call; never visible once the stream has drained */
 };
 
 #define PMNET_MAX_CONFORMERS 128  /* one warp lane per conformer, up to 4 conformers per lane */
@@ -116,6 +118,11 @@ typedef struct PmScoreConfig {
   int32_t scratch_rows;      /* per-warp pair-table capacity in rows; default 8192 */
   int32_t max_conformers;    /* largest n_conf in the batch (default 32): selects 1, 2 or 4 conformers per lane;
                                 ligands with more conformers than the launch was sized for get PMNET_LIG_UNSUPPORTED */
+  int32_t rescore_status;    /* 0: score every ligand. Otherwise only the ligands whose out_status[i] currently equals
+                                this PMNET_LIG_* code are scored (the others keep score and status): re-running the
+                                PMNET_LIG_OVERFLOW ligands of a previous call with a larger scratch needs no host copy
+                                of the library and no compaction */
+  int32_t reserved[3];
 } PmScoreConfig;
 
 int pmnet_abi_version(void);
@@ -132,6 +139,10 @@ size_t pmnet_score_workspace_bytes(int32_t n_model_nodes, int32_t n_model_cluste
  *                     <= 32 / 64 / 128, or NULL
  *   out_status   : [n_ligands] PMNET_LIG_* code
  *   out_stats    : optional [n_ligands * 4] uint32 {tree nodes, leaves, table rows used, pair entries}, or NULL
+ * With an all-default configuration and <= 32 conformers the call enqueues two kernels: the specialised one (all
+ * per-ligand tables in shared memory; csrc/scoring_fast.cuh) and, behind it, the general one for the ligands the first
+ * left PMNET_LIG_DEFERRED. Both compute the same fp32 operations in the same order: results do not depend on which one
+ * scored a ligand. An explicit warps_per_block / blocks / scratch_rows selects the general kernel alone.
  */
 int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const float* weights,
                       float* out_scores, float* out_conf_scores, int32_t* out_status, uint32_t* out_stats,

@@ -27,6 +27,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -37,7 +38,7 @@ namespace {
 constexpr int kMaxDepth = PMNET_MAX_DEPTH;      // levels
 constexpr int kSlots = kMaxDepth + 1;           // depths 0..20 (root = depth 0)
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kMaxClusterNodes = 32;            // model nodes per model cluster handled by the match stream
+constexpr int kMaxClusterNodes = 255;           // matched model nodes per ligand node (M - 1 is stored in 8 bits)
 
 thread_local char g_err[256] = "";
 
@@ -65,8 +66,10 @@ struct WarpLayout {
 // W = 32-conformer words per ligand (1, 2 or 4): every per-conformer row is W * 128 B, every mask W words.
 __host__ __device__ inline WarpLayout make_layout(int n_model_clusters, int scratch_rows, int W) {
   WarpLayout L;
+  // entries: at most 20 levels x Km model clusters. The default / mid configurations cap it at 1024 (more would also
+  // overflow their pair table); the roomy re-run configuration (>= 65536 rows) takes the true worst case
   int t = n_model_clusters * kMaxDepth;
-  if (t > 1024) t = 1024;
+  if (t > 1024 && scratch_rows < 65536) t = 1024;
   L.t_cap = (t + 31) / 32 * 32;
   L.rows = scratch_rows;
   L.pair_cap = scratch_rows * 4;
@@ -161,6 +164,8 @@ struct KernelArgs {
   int scratch_rows;
   int n_cluster_nodes;
   int conf_stride;  // floats per ligand in out_conf (32 * W)
+  int only_status;  // -1: score every ligand; else only the ligands whose out_status holds this code (deferred / re-run)
+  int counter_word; // 32-bit word of the workspace header that is this launch's queue counter
   WarpLayout ly;    // computed once on the host: the kernel reads the offsets from the constant bank
   const float4* edge_g;  // large models: the edge table in the workspace (build_edge_table_kernel)
 };
@@ -216,7 +221,7 @@ __device__ __forceinline__ void pair_term(const SmemModel& sm, const uint8_t* __
       const float s = __fmul_rn(__fsub_rn(d[w], e.x), e.y);
       const float s2 = __fmul_rn(s, s);
       nfail[w] += (s2 < 4.0f) ? 0 : 1;
-      sc[w] += e.w * gauss(s2);
+      sc[w] = fmaf(e.w, gauss(s2), sc[w]);
     }
     return;
   }
@@ -245,7 +250,7 @@ __device__ __forceinline__ void pair_term(const SmemModel& sm, const uint8_t* __
 #pragma unroll
     for (int w = 0; w < W; ++w) {
       nfail[w] += (npass[w] < half) ? 1 : 0;
-      sc[w] += lik[w] * inv;
+      sc[w] = fmaf(lik[w], inv, sc[w]);
     }
     return;
   }
@@ -262,7 +267,7 @@ __device__ __forceinline__ void pair_term(const SmemModel& sm, const uint8_t* __
 #pragma unroll
   for (int w = 0; w < W; ++w) {
     nfail[w] += (npass[w] < ((mn + 1) >> 1)) ? 1 : 0;
-    sc[w] += lik[w] * inv;
+    sc[w] = fmaf(lik[w], inv, sc[w]);
   }
 }
 
@@ -296,6 +301,8 @@ __global__ void build_edge_table_kernel(const EdgeTableArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < a.model.n_nodes * a.model.n_nodes) a.out[i] = edge_entry(a.model, a.w, i, a.model.n_nodes);
 }
+
+#include "scoring_fast.cuh"
 
 template <int W, bool TG>
 __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_kernel(const KernelArgs args) {
@@ -370,18 +377,46 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
   uint8_t* const nmcnt = wbase + LY.off_nmcnt;
   uint8_t* const lnode = wbase + LY.off_lnode;
   uint8_t* const mlist = wbase + LY.off_mlist;
-  unsigned int* const counter = (unsigned int*)args.workspace;
+  unsigned int* const counter = (unsigned int*)args.workspace + args.counter_word;
 
   const PmLigandBatch& B = args.batch;
 
+  // status-driven queue (only_status >= 0): the warp takes 32 queue positions at a time, keeps those whose status
+  // matches, and works through them one by one
+  unsigned pend = 0;
+  unsigned pend_lig = 0;
   for (;;) {
     unsigned int lig = 0;
-    if (lane == 0) {
-      lig = atomicAdd(counter, 1u);
-      if (B.order != nullptr && lig < (unsigned)B.n_ligands) lig = (unsigned)B.order[lig];
+    if (args.only_status < 0) {
+      if (lane == 0) {
+        lig = atomicAdd(counter, 1u);
+        if (B.order != nullptr && lig < (unsigned)B.n_ligands) lig = (unsigned)B.order[lig];
+      }
+      lig = __shfl_sync(kFull, lig, 0);
+      if (lig >= (unsigned)B.n_ligands) break;
+    } else {
+      bool done = false;
+      while (pend == 0u) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(counter, 32u);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= (unsigned)B.n_ligands) {
+          done = true;
+          break;
+        }
+        const unsigned pos = base + lane;
+        bool mine = false;
+        if (pos < (unsigned)B.n_ligands) {
+          pend_lig = B.order != nullptr ? (unsigned)B.order[pos] : pos;
+          mine = args.out_status[pend_lig] == args.only_status;
+        }
+        pend = __ballot_sync(kFull, mine);
+      }
+      if (done) break;
+      const int src = __ffs(pend) - 1;
+      pend &= pend - 1;
+      lig = __shfl_sync(kFull, pend_lig, src);
     }
-    lig = __shfl_sync(kFull, lig, 0);
-    if (lig >= (unsigned)B.n_ligands) break;
 
     const int C = B.n_conf[lig];
     float score_out = 0.0f;
@@ -1122,7 +1157,7 @@ int sm_count_cached() {
 int conf_words(int max_conformers) { return max_conformers <= 32 ? 1 : (max_conformers <= 64 ? 2 : 4); }
 
 void resolve_cfg(const PmScoreConfig* in, PmScoreConfig* out, bool query_device) {
-  PmScoreConfig c = {0, 0, 0, 0};
+  PmScoreConfig c = {};
   if (in) c = *in;
   if (c.max_conformers <= 0) c.max_conformers = 32;
   const int W = conf_words(c.max_conformers);
@@ -1133,6 +1168,23 @@ void resolve_cfg(const PmScoreConfig* in, PmScoreConfig* out, bool query_device)
   if (c.scratch_rows <= 0) c.scratch_rows = 8192;
   *out = c;
 }
+
+// The specialised kernel runs first when the caller left the launch shape to the library, every ligand has at most 32
+// conformers, nothing restricts the call to a status and the model tables fit in shared memory next to the per-warp
+// tables. PMNET_NO_FAST=1 in the environment forces the general kernel (A/B measurements).
+bool use_fast_kernel(const PmScoreConfig* in, int n_nodes, int n_clusters, int n_cluster_nodes) {
+  static const bool disabled = [] {
+    const char* e = getenv("PMNET_NO_FAST");
+    return e && e[0] && e[0] != '0';
+  }();
+  if (disabled) return false;
+  if (in && (in->warps_per_block > 0 || in->blocks > 0 || in->scratch_rows > 0 || in->rescore_status != 0)) return false;
+  if (in && in->max_conformers > 32) return false;
+  if (n_cluster_nodes < 0) n_cluster_nodes = n_nodes > n_clusters ? 4 * n_nodes : 4 * n_clusters;  // sizing query: a bound
+  return fastk::smem_bytes(n_nodes, n_clusters, n_cluster_nodes) <= fastk::kSmemMax;
+}
+
+size_t fast_workspace_bytes() { return kHeaderBytes + (size_t)sm_count_cached() * fastk::kWarps * fastk::G_BYTES; }
 
 }  // namespace
 
@@ -1151,7 +1203,10 @@ size_t pmnet_score_workspace_bytes(int32_t n_model_nodes, int32_t n_model_cluste
   const WarpLayout L = make_layout(n_model_clusters, c.scratch_rows, conf_words(c.max_conformers));
   // + room for the edge table of a large model (used when the tables do not fit in shared memory)
   const size_t edge = align_up((size_t)(n_model_nodes > 0 ? n_model_nodes : 0) * (size_t)(n_model_nodes > 0 ? n_model_nodes : 0) * 16, 256);
-  return kHeaderBytes + (size_t)c.blocks * c.warps_per_block * L.bytes + edge;
+  size_t need = kHeaderBytes + (size_t)c.blocks * c.warps_per_block * L.bytes + edge;
+  // the specialised kernel's scratch aliases the general kernel's (they run one after the other on the stream)
+  if (use_fast_kernel(cfg, n_model_nodes, n_model_clusters, -1) && fast_workspace_bytes() > need) need = fast_workspace_bytes();
+  return need;
 }
 
 int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const float* weights, float* out_scores,
@@ -1177,7 +1232,8 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
   }
   PmScoreConfig c;
   resolve_cfg(cfg, &c, true);
-  const size_t need = pmnet_score_workspace_bytes(model->n_nodes, model->n_clusters, &c);
+  // sized with the caller's configuration: an all-default one also reserves the specialised kernel's scratch
+  const size_t need = pmnet_score_workspace_bytes(model->n_nodes, model->n_clusters, cfg);
   if (workspace_bytes < need) {
     set_err("pmnet_score_batch: workspace too small");
     return PMNET_EWORKSPACE;
@@ -1215,6 +1271,41 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
     set_err("pmnet_score_batch: per-node / per-cluster model arrays do not fit in shared memory");
     return PMNET_ELIMIT;
   }
+  // ---- the specialised kernel first (csrc/scoring_fast.cuh); what it defers is picked up by the general kernel below
+  const bool fast = W == 1 && !tg && use_fast_kernel(cfg, model->n_nodes, model->n_clusters, n_cluster_nodes);
+  a.only_status = (cfg && cfg->rescore_status != 0) ? cfg->rescore_status : -1;
+  a.counter_word = 0;
+  e = cudaMemsetAsync(workspace, 0, kHeaderBytes, stream);
+  if (e != cudaSuccess) {
+    set_err(cudaGetErrorString(e));
+    return PMNET_ECUDA;
+  }
+  if (fast) {
+    fastk::FastArgs fa;
+    fa.model = *model;
+    fa.batch = *batch;
+    for (int i = 0; i < PMNET_NUM_TYPES; ++i) fa.w[i] = weights[i];
+    fa.out_scores = out_scores;
+    fa.out_conf = out_conf_scores;
+    fa.out_status = out_status;
+    fa.out_stats = out_stats;
+    fa.workspace = (unsigned char*)workspace;
+    fa.n_cluster_nodes = n_cluster_nodes;
+    const size_t fsmem = fastk::smem_bytes(model->n_nodes, model->n_clusters, n_cluster_nodes);
+    e = cudaFuncSetAttribute(fastk::pmnet_score_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+    if (e != cudaSuccess) {
+      set_err(cudaGetErrorString(e));
+      return PMNET_ECUDA;
+    }
+    fastk::pmnet_score_fast_kernel<<<sm_count_cached(), fastk::kWarps * 32, fsmem, stream>>>(fa);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_err(cudaGetErrorString(e));
+      return PMNET_ECUDA;
+    }
+    a.only_status = PMNET_LIG_DEFERRED;
+    a.counter_word = 2;
+  }
   a.edge_g = nullptr;
   if (tg) {
     // the edge table sits behind the per-warp scratch (pmnet_score_workspace_bytes reserves it)
@@ -1232,7 +1323,6 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
   else if (W == 2) fn = tg ? (const void*)pmnet_score_kernel<2, true> : (const void*)pmnet_score_kernel<2, false>;
   else fn = tg ? (const void*)pmnet_score_kernel<4, true> : (const void*)pmnet_score_kernel<4, false>;
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaMemsetAsync(workspace, 0, kHeaderBytes, stream);
   if (e != cudaSuccess) {
     set_err(cudaGetErrorString(e));
     return PMNET_ECUDA;

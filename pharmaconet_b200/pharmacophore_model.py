@@ -238,7 +238,17 @@ class PharmacophoreModel:
             batch = LigandBatch.from_reference_graphs([ligand.graph])
         else:
             raise TypeError("ligand must be a TypedLigand or expose a reference-style .graph")
-        return float(self.scoring_batch(batch, weights)[0])
+        from . import _abi
+        from .scoring import score_library
+
+        out = score_library(self.device_model("cuda"), batch, weights)
+        if int(out["status"][0]) >= _abi.LIG_OVERFLOW:
+            # the reference would compute a real score here: do not hand back a silent 0
+            raise RuntimeError(
+                "ligand could not be scored on the device (more than 128 conformers, or a pair table beyond the largest "
+                "scratch configuration)"
+            )
+        return float(out["scores"][0])
 
     def scoring_pbmol(self, ligand_pbmol, atom_positions, conformer_axis: int | None = None, weights=None) -> float:
         from .ligand_typing import typed_ligand_from_pbmol

@@ -7,7 +7,8 @@
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
+import warnings
+from dataclasses import dataclass, replace
 
 import numpy as np
 import torch
@@ -95,9 +96,12 @@ class ScoreConfig:
     warps_per_block: int = 0  # 0 = library default
     blocks: int = 0
     scratch_rows: int = 0
+    rescore_status: int = 0  # != 0: only ligands whose status holds this code are scored (in-place re-runs)
 
     def struct(self, max_conformers: int = 32) -> _abi.PmScoreConfig:
-        return _abi.PmScoreConfig(self.warps_per_block, self.blocks, self.scratch_rows, int(max_conformers))
+        return _abi.PmScoreConfig(
+            self.warps_per_block, self.blocks, self.scratch_rows, int(max_conformers), int(self.rescore_status)
+        )
 
 
 def conf_stride(max_conformers: int) -> int:
@@ -120,20 +124,45 @@ def mid_config(model) -> ScoreConfig:
     return ScoreConfig(warps_per_block=16, blocks=0, scratch_rows=32768)
 
 
+def warn_unscored(status: torch.Tensor, what: str) -> int:
+    """Ligands that no configuration could score keep score 0; say so instead of returning a silent 0."""
+    n_bad = int((status >= _abi.LIG_OVERFLOW).sum().item())
+    if n_bad:
+        warnings.warn(
+            f"{what}: {n_bad} ligand(s) could not be scored (status OVERFLOW / UNSUPPORTED after the last retry: more "
+            f"than {_abi.MAX_CONFORMERS} conformers, or a pair table beyond the largest scratch); their score is 0",
+            RuntimeWarning,
+            stacklevel=3,
+        )
+    return n_bad
+
+
+def rescore_overflowed_device(
+    model: "DeviceModel", batch: "DeviceLigandBatch", out: dict, weights=None, stream: torch.cuda.Stream | None = None
+) -> int:
+    """Re-run, IN PLACE on the device-resident `batch`, the ligands that a previous `score_batch` left with status
+    OVERFLOW: `mid_config` first, `big_config` for what still does not fit (C-ABI PmScoreConfig.rescore_status: the
+    kernel's queue skips every other ligand, so no host copy of the library and no compaction is needed).
+    `out` = the dict returned by score_batch; its tensors are updated. Returns the number of ligands re-run."""
+    n_over = int((out["status"] == _abi.LIG_OVERFLOW).sum().item())
+    if n_over == 0:
+        return 0
+    for cfg in (mid_config(model), big_config(model)):
+        score_batch(
+            model, batch, weights, replace(cfg, rescore_status=_abi.LIG_OVERFLOW), out_scores=out["scores"],
+            out_status=out["status"], out_stats=out.get("stats"), out_conf=out.get("conf"), stream=stream,
+        )  # fmt: skip
+        if not bool((out["status"] == _abi.LIG_OVERFLOW).any().item()):
+            break
+    return n_over
+
+
 def rescore_overflowed(model: "DeviceModel", sub: LigandBatch, weights=None, with_stats: bool = False) -> dict:
-    """Score ligands whose pair table overflowed the default per-warp scratch: `mid_config` first, `big_config` for
-    what still does not fit. `sub` is a host batch of just those ligands; returns device tensors like score_batch."""
+    """Score a HOST batch of ligands whose pair table overflowed the default per-warp scratch (streamed screening:
+    their block has left the device by the time the status is read). Returns device tensors like score_batch."""
     dev_sub = DeviceLigandBatch.from_host(sub, model.device)
     out = score_batch(model, dev_sub, weights, mid_config(model), with_stats=with_stats)
-    still = torch.nonzero(out["status"] == _abi.LIG_OVERFLOW).flatten()
-    if still.numel():
-        idx = still.cpu().numpy()
-        o2 = score_batch(
-            model, DeviceLigandBatch.from_host(sub.select(idx), model.device), weights, big_config(model),
-            with_stats=with_stats,
-        )  # fmt: skip
-        for k in out:
-            out[k][still] = o2[k]
+    rescore_overflowed_device(model, dev_sub, out, weights)
     return out
 
 
@@ -170,6 +199,8 @@ def score_batch(
     with_conf: bool = False,
     stream: torch.cuda.Stream | None = None,
     workspace: torch.Tensor | None = None,
+    out_stats: torch.Tensor | None = None,
+    out_conf: torch.Tensor | None = None,
 ):
     """Enqueue one scoring launch on `stream` (default: torch's current stream). Returns a dict of device tensors:
     scores f32[n], status i32[n] (+ stats u32[n,4] -> {tree nodes, leaves, rows, pair entries}; conf f32[n,32])."""
@@ -189,8 +220,12 @@ def score_batch(
                 raise RuntimeError(f"workspace of {ws.numel()} bytes is too small ({need} needed)")
         scores = out_scores if out_scores is not None else torch.empty(n, dtype=torch.float32, device=dev)
         status = out_status if out_status is not None else torch.empty(n, dtype=torch.int32, device=dev)
-        stats = torch.zeros((n, 4), dtype=torch.int32, device=dev) if with_stats else None
-        conf = torch.zeros((n, conf_stride(batch.max_conformers)), dtype=torch.float32, device=dev) if with_conf else None
+        with_stats = with_stats or out_stats is not None
+        with_conf = with_conf or out_conf is not None
+        stats = out_stats if out_stats is not None else (torch.zeros((n, 4), dtype=torch.int32, device=dev) if with_stats else None)
+        conf = out_conf
+        if conf is None and with_conf:
+            conf = torch.zeros((n, conf_stride(batch.max_conformers)), dtype=torch.float32, device=dev)
         w = (C.c_float * 7)(*weights_vector(weights))
         s = stream if stream is not None else torch.cuda.current_stream(dev)
         rc = L.pmnet_score_batch(
@@ -214,20 +249,15 @@ def score_library(
     config: ScoreConfig | None = None,
     with_stats: bool = False,
 ) -> dict[str, np.ndarray]:
-    """Score a host-resident library chunk: H2D, one launch, re-run of overflowed ligands with BIG_CONFIG, D2H.
-    Returns numpy arrays (scores f32, status i32[, stats])."""
+    """Score a host-resident library chunk: H2D, one launch, in-place re-run of the overflowed ligands with the roomier
+    configurations, D2H. Returns numpy arrays (scores f32, status i32[, stats])."""
     dev_batch = DeviceLigandBatch.from_host(host_batch, model.device)
     out = score_batch(model, dev_batch, weights, config, with_stats=with_stats)
+    rescore_overflowed_device(model, dev_batch, out, weights)
+    warn_unscored(out["status"], "score_library")
     scores = out["scores"].cpu().numpy()
     status = out["status"].cpu().numpy()
     stats = out["stats"].cpu().numpy().view(np.uint32) if with_stats else None
-    over = np.nonzero(status == _abi.LIG_OVERFLOW)[0]
-    if len(over):
-        o2 = rescore_overflowed(model, host_batch.select(over), weights, with_stats=with_stats)
-        scores[over] = o2["scores"].cpu().numpy()
-        status[over] = o2["status"].cpu().numpy()
-        if with_stats:
-            stats[over] = o2["stats"].cpu().numpy().view(np.uint32)
     res = dict(scores=scores, status=status)
     if with_stats:
         res["stats"] = stats

@@ -21,7 +21,7 @@ from . import _abi
 from .packing import LigandBatch, PackedModel
 from .scoring import (
     DeviceLigandBatch, DeviceModel, ScoreConfig, cost_order, order_workspace_bytes as _lib_order_bytes, rescore_overflowed,
-    score_batch, topk, workspace_bytes,
+    rescore_overflowed_device, score_batch, topk, warn_unscored, workspace_bytes,
 )  # fmt: skip
 
 
@@ -154,13 +154,18 @@ class Screener:
 
     # ------------------------------------------------------------------ device-resident shard: one launch
     def screen_device(self, batch: DeviceLigandBatch, id_base: int = 0, gather: bool = True) -> ScreenResult:
-        launches = 3  # scoring kernel + id fill + top-k write-out (the radix sort passes are CUB's)
+        launches = 4  # two scoring kernels (specialised + general) + id fill + top-k write-out (the sort passes are CUB's)
         if self.lpt and batch.order is None:
             # once per resident library and model: the order only depends on topologies and the model's cluster types
             batch.set_order(cost_order(self.model, batch))
             launches += 1
         out = self._timed_score(batch)
-        n_over = 0
+        # ligands whose pair table overflowed the default scratch are re-run in place with the roomier configurations
+        # (one device->host read of the overflow count; nothing else leaves the device)
+        n_over = rescore_overflowed_device(self.model, batch, out, self.weights)
+        if n_over:
+            launches += 1
+            warn_unscored(out["status"], "screen_device")
         ks, ki = topk(out["scores"], self.k, id_base)
         if gather:
             ks, ki = gather_topk(ks, ki, self.k)
@@ -244,7 +249,8 @@ class Screener:
             nb = b - a
             nc = int(lib.n_conf[a:b].sum())
             n_conf += nc
-            db = DeviceLigandBatch(views, nb, nc, bases, max_conformers=int(lib.n_conf[a:b].max()))
+            # the library-wide maximum for every block: one kernel instantiation and one workspace layout per screen
+            db = DeviceLigandBatch(views, nb, nc, bases, max_conformers=max(1, lib.max_conformers))
             if it < self.n_slots:
                 slot.stream.wait_event(start)
             slot.stream.wait_event(slot.ready)
@@ -262,7 +268,7 @@ class Screener:
             )  # fmt: skip
             slot.free.record(slot.stream)
             spans.append((pos, nb, a))
-            launches += 1 + int(self.lpt)
+            launches += 2 + int(self.lpt)
             pos += nb
         for slot in (self._slots or [])[: len(blocks)]:
             main.wait_event(slot.free)
@@ -278,6 +284,7 @@ class Screener:
         if len(over):
             sub = lib.select(ids[over])
             o2 = rescore_overflowed(self.model, sub, self.weights)
+            warn_unscored(o2["status"], "screen_host")
             scores[torch.from_numpy(over).to(dev)] = o2["scores"]
             launches += 1
             over_ids = torch.from_numpy(ids[over]).to(dev)
@@ -313,8 +320,8 @@ def screen_models(
     The library stays in HBM; every model is one scoring launch plus a top-k, alternating between two streams with
     their own scratch so that the long-ligand tail of one model's persistent grid overlaps the start of the next.
     There is no host synchronisation until all models are enqueued. Ligands whose pair table overflowed the per-warp
-    scratch are re-run with the roomy configuration when `host_lib` (the same shard on the host) is given; otherwise
-    their count is reported in `n_overflow` and their score is 0.
+    scratch are re-run in place on the resident shard with the roomier configurations (`host_lib` is accepted for
+    backward compatibility and not needed any more); `n_overflow` reports how many.
     """
     dev = batch.device
     cfg = config or ScoreConfig()
@@ -351,13 +358,11 @@ def screen_models(
         main.wait_stream(st)
     results = []
     for dm, (o, ks, ki) in zip(dms, outs):
-        over = torch.nonzero(o["status"] == _abi.LIG_OVERFLOW).flatten()  # (first host sync of the call)
-        n_over = int(over.numel())
+        # (first host sync of the call) overflowed ligands are re-run in place on the resident shard
+        n_over = rescore_overflowed_device(dm, batch, o, weights)
         launches = 4
-        if n_over and host_lib is not None:
-            sub = host_lib.select(over.cpu().numpy())
-            o2 = rescore_overflowed(dm, sub, weights)
-            o["scores"][over] = o2["scores"]
+        if n_over:
+            warn_unscored(o["status"], "screen_models")
             ks, ki = topk(o["scores"], k, id_base)
             launches += 3
         if gather:

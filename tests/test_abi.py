@@ -36,10 +36,10 @@ def test_abi_version_and_host_only_calls():
 
 
 def test_struct_layouts_match_header():
-    # 4 x int32 + 8 pointers; int32 + pad + 8 pointers + int64 + 4 x int32; 4 x int32
+    # 4 x int32 + 8 pointers; int32 + pad + 8 pointers + int64 + 4 x int32; 8 x int32 (ABI 3: rescore_status + 3 reserved)
     assert ctypes.sizeof(_abi.PmModel) == 16 + 8 * 8
     assert ctypes.sizeof(_abi.PmLigandBatch) == 8 + 8 * 8 + 24 + 8  # + the optional `order` pointer (ABI 2)
-    assert ctypes.sizeof(_abi.PmScoreConfig) == 16
+    assert ctypes.sizeof(_abi.PmScoreConfig) == 32
 
 
 def test_null_arguments_are_rejected_without_a_gpu():

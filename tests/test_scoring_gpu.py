@@ -360,3 +360,76 @@ def test_large_model_tables_in_global_memory():
     db = scoring.DeviceLigandBatch.from_host(batch, "cuda:0")
     res = screening.screen_models([pm, load_case("syn0_c8")["model"]], db, host_lib=batch, k=16, keep_scores=True)
     assert rel_err(res[0].scores.cpu().numpy(), ref["scores"]).max() <= REL_TOL
+
+
+def test_specialised_and_general_kernel_agree_bit_for_bit():
+    """Default configuration = specialised kernel (+ general kernel for what it defers); an explicit launch shape =
+    general kernel alone. Same fp32 operations in the same order: identical scores, statuses and tree shapes."""
+    c = load_case("syn0_c32")
+    batch = LigandBatch.from_typed(synthetic.make_ligands(3000, 32, seed=211) + synthetic.make_ligands(200, 7, seed=212, frag_range=(9, 15)))
+    a = _run(c["model"], batch, None)
+    b = _run(c["model"], batch, None, config=scoring.ScoreConfig(32, 148, 8192))
+    assert np.array_equal(a["status"], b["status"]) and np.all(a["status"] <= _abi.LIG_EMPTY)
+    assert np.array_equal(a["scores"], b["scores"])
+    assert np.array_equal(a["stats"][:, [0, 1, 3]], b["stats"][:, [0, 1, 3]])
+    o = orc.score(c["model"], batch, None)
+    assert rel_err(a["scores"], o["scores"]).max() <= REL_TOL
+    assert np.array_equal(a["stats"][:, 0].astype(np.uint64), o["stats"][:, 0])
+
+
+def test_no_ligand_is_left_deferred():
+    """Ligands beyond the specialised kernel's caps (many clusters, wide model) are finished by the general kernel in the
+    same call: PMNET_LIG_DEFERRED never reaches the caller."""
+    for name in ("syn0_c4_deep", "syn0_c5_big", "loose_c8"):
+        c = load_case(name)
+        dm = scoring.DeviceModel(c["model"], "cuda:0")
+        out = scoring.score_batch(dm, scoring.DeviceLigandBatch.from_host(c["batch"], "cuda:0"))
+        st = out["status"].cpu().numpy()
+        assert not np.any(st == _abi.LIG_DEFERRED)
+
+
+def test_screen_device_reruns_overflow_in_place():
+    from pharmaconet_b200 import screening
+
+    c = load_case("syn0_c5_big")
+    scr = screening.Screener(c["model"], "cuda:0", k=8, config=scoring.ScoreConfig(4, 8, 64))
+    res = scr.screen_device(scoring.DeviceLigandBatch.from_host(c["batch"], "cuda:0"))
+    assert res.n_overflow > 0
+    assert rel_err(res.scores.cpu().numpy(), c["ref"]).max() <= REL_TOL
+    order = np.lexsort((np.arange(len(c["ref"])), -res.scores.cpu().numpy().astype(np.float64)))[:8]
+    assert np.array_equal(res.topk_ids.cpu().numpy(), order)
+
+
+def test_rescore_status_only_touches_matching_ligands():
+    c = load_case("syn0_c8")
+    dm = scoring.DeviceModel(c["model"], "cuda:0")
+    db = scoring.DeviceLigandBatch.from_host(c["batch"], "cuda:0")
+    out = scoring.score_batch(dm, db)
+    ref = out["scores"].clone()
+    # pretend three ligands overflowed and wipe their scores: only they are recomputed
+    idx = torch.tensor([3, 17, 90], device="cuda:0")
+    out["status"][idx] = _abi.LIG_OVERFLOW
+    out["scores"][:] = -1.0
+    n = scoring.rescore_overflowed_device(dm, db, out)
+    assert n == 3
+    s = out["scores"].cpu().numpy()
+    assert np.array_equal(s[idx.cpu().numpy()], ref[idx].cpu().numpy())
+    keep = np.ones(len(s), bool)
+    keep[idx.cpu().numpy()] = False
+    assert np.all(s[keep] == -1.0)
+
+
+def test_streamed_screening_mixed_conformer_counts():
+    """A library whose blocks differ in their largest conformer count (8 vs 40): every block uses the library-wide
+    maximum, so one kernel instantiation and one workspace layout serve the whole screen."""
+    from pharmaconet_b200 import screening
+
+    c = load_case("syn0_c32")
+    ligs = synthetic.make_ligands(300, 8, seed=301) + synthetic.make_ligands(60, 40, seed=302) + synthetic.make_ligands(200, 8, seed=303)
+    batch = LigandBatch.from_typed(ligs)
+    whole = _run(c["model"], batch, None)["scores"]
+    scr = screening.Screener(c["model"], "cuda:0", k=20, block_ligands=128, ramp=False)
+    res = scr.screen_host(batch)
+    assert np.array_equal(res.scores, whole)
+    o = orc.score(c["model"], batch, None)
+    assert rel_err(res.scores, o["scores"]).max() <= REL_TOL
