@@ -179,6 +179,20 @@ int pmnet_conv3d_k3_c96(const void* x_c8, const void* w_packed, const float* sca
                         const float* head_w, float head_b, float* head_out, int32_t B, int32_t D, int32_t H,
                         int32_t W, int32_t relu, int32_t planes_per_item, int32_t max_ctas, void* stream);
 
+/* One pass of a split-precision convolution (same kernel, same layouts). With activations and weights split into bf16
+ * pairs x = x_hi + x_lo, w = w_hi + w_lo the product x w = x_hi w_hi + x_lo w_hi + x_hi w_lo (+ 2^-16 relative) is
+ * three launches that chain their fp32 accumulators through global memory:
+ *   acc_in  : fp32 [B][D][H][W][96] partial sums of the earlier passes (NULL for the first pass)
+ *   acc_out : not NULL = store the raw fp32 sum there (may alias acc_in) and skip activation and outputs
+ *   the last pass (acc_out NULL) applies scale / bias / ReLU / head to the full sum and writes y_c8 = bf16(y) and, if
+ *   y_lo_c8 is given, y_lo_c8 = bf16(y - y_c8): the operand pair of the next layer.
+ * This is the opt-in precision mode for outputs that feed a threshold (cavity / segmentation masks, module.py:232-233,
+ * 288): with plain bf16 operands a few hundred of 262144 mask voxels flip against the fp32 reference. */
+int pmnet_conv3d_k3_c96_pass(const void* x_c8, const void* w_packed, const float* scale, const float* bias, void* y_c8,
+                             void* y_lo_c8, const float* acc_in, float* acc_out, const float* head_w, float head_b,
+                             float* head_out, int32_t B, int32_t D, int32_t H, int32_t W, int32_t relu,
+                             int32_t planes_per_item, int32_t max_ctas, void* stream);
+
 /* FPNDecoder lateral (decoders/fpn_decoder.py:100-111): out = act(scale * (W x) + bias) + nearest_upsample(up).
  *   x      : fp32 [B][C_in][D][H][W] (x_is_c8 = 0) or bf16 c8 [B][C_in/8][D][H][W][8] (x_is_c8 = 1)
  *   w_t    : fp32 [C_in][96] (the 1x1 conv weight, transposed); scale/bias fp32 [96] or NULL for a raw linear map
@@ -186,6 +200,12 @@ int pmnet_conv3d_k3_c96(const void* x_c8, const void* w_packed, const float* sca
 int pmnet_lateral_c96(const void* x, int32_t x_is_c8, int32_t c_in, const float* w_t, const float* scale,
                       const float* bias, int32_t relu, const void* up_c8, void* out_c8, int32_t B, int32_t D,
                       int32_t H, int32_t W, void* stream);
+
+/* Same with two-term bf16 splits (x = x + x_lo when x_is_c8, up = up + up_lo; out = bf16(y), out_lo = bf16(y - out));
+ * any of the *_lo pointers may be NULL. */
+int pmnet_lateral_c96_split(const void* x, const void* x_lo, int32_t x_is_c8, int32_t c_in, const float* w_t,
+                            const float* scale, const float* bias, int32_t relu, const void* up_c8, const void* up_lo_c8,
+                            void* out_c8, void* out_lo_c8, int32_t B, int32_t D, int32_t H, int32_t W, void* stream);
 
 /* MaskHead.get_box_features (mask_head.py:170-196) pushed through the linear lateral conv: for every box j of a group
  *   out[j] = act(scale * (S + u[j] + [voxel in pvox] pvec[j]) + bias) + nearest_upsample(up[j])
@@ -197,6 +217,11 @@ int pmnet_lateral_c96(const void* x, int32_t x_is_c8, int32_t c_in, const float*
 int pmnet_box_combine_c96(const void* s_c8, const float* u, const float* pvec, const int32_t* pvox,
                           const float* scale, const float* bias, int32_t relu, const void* up_c8, void* out_c8,
                           int32_t nbox, int32_t D, int32_t H, int32_t W, void* stream);
+
+int pmnet_box_combine_c96_split(const void* s_c8, const void* s_lo_c8, const float* u, const float* pvec,
+                                const int32_t* pvox, const float* scale, const float* bias, int32_t relu,
+                                const void* up_c8, const void* up_lo_c8, void* out_c8, void* out_lo_c8, int32_t nbox,
+                                int32_t D, int32_t H, int32_t W, void* stream);
 
 /* Density-map post-processing (module.py:277-288): sigmoid(logits) masked to box & protein & cavity, 5^3 Gaussian
  * smoothing with zero padding (utils/smoothing.py), masked again, values < threshold set to 0. The spherical box area of

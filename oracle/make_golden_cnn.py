@@ -29,6 +29,7 @@ from pharmaconet_b200 import cnn_weights  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 SEED = 0
+NEAR = 5e-3  # |logit| band recorded next to the mask bits
 
 
 def main():
@@ -75,6 +76,11 @@ def main():
         for name, t in (("narrow", narrow), ("wide", wide)):
             out[f"cavity_{name}_f16_s4"] = t[0, 0, ::4, ::4, ::4].numpy().astype(np.float16)
             out[f"cavity_{name}_bits"] = np.packbits((t[0, 0] > 0).numpy())
+            # voxels whose fp32 logit lies within 5e-3 of the threshold: where a result that differs from this CPU run by
+            # fp32-level rounding (summation order) may legitimately land on the other side
+            near = torch.nonzero(t[0, 0].reshape(-1).abs() < NEAR).reshape(-1)
+            out[f"cavity_{name}_near_idx"] = near.numpy().astype(np.int32)
+            out[f"cavity_{name}_near_val"] = t[0, 0].reshape(-1)[near].numpy()
         scores, tfeat = model.forward_token_prediction(feats[-1], [tokens])
         out["token_scores"] = scores[0].numpy()
         out["token_features"] = tfeat[0].numpy()
@@ -82,6 +88,10 @@ def main():
         seg = model.forward_segmentation(feats, [hot], [tfeat[0][:4]])[0][0]  # [4, 64, 64, 64] logits
         out["seg_f16_s4"] = seg[:, ::4, ::4, ::4].numpy().astype(np.float16)
         out["seg_bits"] = np.packbits((seg > 0).numpy())
+        near = torch.nonzero(seg.reshape(-1).abs() < NEAR).reshape(-1)
+        out["seg_near_idx"] = near.numpy().astype(np.int32)
+        out["seg_near_val"] = seg.reshape(-1)[near].numpy()
+        out["seg_rms"] = np.float64(seg.pow(2).mean().sqrt().item())
         # reference post-processing (module.py:277-288) on seeded logits / masks (regenerated from the seeds in the test)
         gm = torch.Generator().manual_seed(SEED + 1)
         post_logits = torch.randn((4, 64, 64, 64), generator=gm) * 3.0 + 1.0

@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("PMNET_B200_SO") or os.path.join(_PKG, "libpmnet_b200.so")  # env override: developer A/B builds
 SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("scoring.cu", "conv3d.cu", "pointwise.cu", "swin_ops.cu")]
-HEADERS = [os.path.join(_ROOT, "include", "pmnet_b200.h")]
+HEADERS = [os.path.join(_ROOT, "include", "pmnet_b200.h"), os.path.join(_PKG, "csrc", "scoring_fast.cuh")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC",
@@ -44,15 +44,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libpmnet_b200.so")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", SO_PATH + ".tmp", *SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{r.stdout}\n{r.stderr}")
-    os.replace(SO_PATH + ".tmp", SO_PATH)
-    if verbose:
-        print(r.stderr)
+    import fcntl
+
+    # one builder at a time (several ranks of a fresh checkout may get here together); every builder writes its own
+    # temporary file and the finished library is moved into place atomically
+    with open(SO_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():  # another process built it while this one waited
+                return SO_PATH
+            tmp = f"{SO_PATH}.{os.getpid()}.tmp"
+            cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, *SOURCES]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed:\n{r.stdout}\n{r.stderr}")
+            os.replace(tmp, SO_PATH)
+            if verbose:
+                print(r.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO_PATH
 
 
@@ -60,7 +72,7 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(SO_PATH):
+    if is_stale() and _nvcc() is not None:  # missing, or older than a source / header (an edited .cu must not run stale)
         build()
     L = C.CDLL(SO_PATH)
     L.pmnet_abi_version.restype = C.c_int
@@ -90,6 +102,21 @@ def lib() -> C.CDLL:
     L.pmnet_conv3d_k3_c96.argtypes = [
         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+    ]  # fmt: skip
+    L.pmnet_conv3d_k3_c96_pass.restype = C.c_int
+    L.pmnet_conv3d_k3_c96_pass.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+        C.c_float, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+    ]  # fmt: skip
+    L.pmnet_lateral_c96_split.restype = C.c_int
+    L.pmnet_lateral_c96_split.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+    ]  # fmt: skip
+    L.pmnet_box_combine_c96_split.restype = C.c_int
+    L.pmnet_box_combine_c96_split.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
     ]  # fmt: skip
     L.pmnet_lateral_c96.restype = C.c_int
     L.pmnet_lateral_c96.argtypes = [
@@ -136,8 +163,11 @@ EXPORTS = (
     "pmnet_topk_workspace_bytes",
     "pmnet_topk",
     "pmnet_conv3d_k3_c96",
+    "pmnet_conv3d_k3_c96_pass",
     "pmnet_lateral_c96",
+    "pmnet_lateral_c96_split",
     "pmnet_box_combine_c96",
+    "pmnet_box_combine_c96_split",
     "pmnet_density_post",
     "pmnet_window_attention",
     "pmnet_ln_residual",

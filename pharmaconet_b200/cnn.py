@@ -46,15 +46,18 @@ class _ConvBN:
         self.weight = w
         if self.kernel == 3 and self.cin == 96 and w.shape[0] == 96:
             self.packed = conv.pack_weights_k3(w)
+            w_hi, w_lo = conv.split_bf16(w)  # two-term split for the split-precision mode
+            self.packed_lo = conv.pack_weights_k3(w_lo)
+            assert torch.equal(self.packed, conv.pack_weights_k3(w_hi))
         elif self.kernel == 1:
             self.w_t = w.reshape(w.shape[0], self.cin).t().contiguous().float()  # [C_in][C_out]
 
 
 class Features(tuple):
     """multi-scale features, top-down, as NCDHW fp32 tensors (the reference's return type); `.c8` keeps the bf16
-    chunked copies the kernels consume so that later stages do not convert again."""
+    chunked activations (conv.Act) the kernels consume so that later stages do not convert again."""
 
-    c8: list[torch.Tensor]
+    c8: list
 
 
 class PharmacoNetModel:
@@ -79,14 +82,29 @@ class PharmacoNetModel:
         self.mask_logit_w = sd["mask_head.conv_logits.weight"].reshape(96).float().contiguous()
         self.mask_logit_b = float(sd["mask_head.conv_logits.bias"].item())
         self._L = _lib.lib()
+        # "bf16": every convolution is one tcgen05 pass on bf16 operands (fastest; ~2^-8 relative error per layer, a
+        # few hundred of 262144 mask voxels differ from the fp32 reference). "bf16x3": activations and weights of the
+        # convolution stack travel as two-term bf16 splits and every convolution is three passes (~2^-16 relative
+        # error per product): the precision mode for outputs that feed a threshold (module.py:232-233, 288).
+        self.precision = "bf16"
+
+    @property
+    def split(self) -> bool:
+        return self.precision == "bf16x3"
 
     # ------------------------------------------------------------------ kernels
-    def _k3(self, x_c8, layer: _ConvBN, head=None, store_out=True):
+    def _k3(self, x: "conv.Act", layer: _ConvBN, head=None, store_out=True):
         hw, hb = head if head is not None else (None, 0.0)
-        return conv.conv3d_k3_c96(x_c8, layer.packed, layer.scale, layer.bias, True, hw, hb, store_out)
+        if x.lo is not None:
+            return conv.conv3d_k3_c96_x3(x, layer.packed, layer.packed_lo, layer.scale, layer.bias, True, hw, hb, store_out)
+        y, h = conv.conv3d_k3_c96(x.hi, layer.packed, layer.scale, layer.bias, True, hw, hb, store_out)
+        return (conv.Act(y) if y is not None else None), h
 
-    def _lateral(self, x, x_is_c8: bool, layer: _ConvBN, up_c8, affine=True):
+    def _lateral(self, x, x_is_c8: bool, layer: _ConvBN, up: "conv.Act | None", affine=True, split=None) -> "conv.Act":
+        split = self.split if split is None else split
+        x_lo = None
         if x_is_c8:
+            x, x_lo = x.hi, x.lo
             B, _, D, H, W, _ = x.shape
         else:
             B, _, D, H, W = x.shape
@@ -96,30 +114,35 @@ class PharmacoNetModel:
                 # - a plain library GEMM plus a few tiny elementwise ops is faster than the fused kernel here
                 y = torch.einsum("bcv,oc->bov", x.reshape(B, layer.cin, -1), layer.w_t.t()).reshape(B, 96, D, H, W)
                 y = torch.relu(y * layer.scale.view(1, -1, 1, 1, 1) + layer.bias.view(1, -1, 1, 1, 1))
-                if up_c8 is not None:
-                    y = y + F.interpolate(conv.from_c8(up_c8), scale_factor=2, mode="nearest")
-                return conv.to_c8(y)
+                if up is not None:
+                    y = y + F.interpolate(up.float_ncdhw(), scale_factor=2, mode="nearest")
+                return conv.to_act(y, split)
         out = torch.empty((B, 12, D, H, W, 8), dtype=torch.bfloat16, device=self.device)
-        rc = self._L.pmnet_lateral_c96(
-            x.data_ptr(), int(x_is_c8), layer.cin, layer.w_t.data_ptr(),
+        out_lo = torch.empty_like(out) if split else None
+        rc = self._L.pmnet_lateral_c96_split(
+            x.data_ptr(), x_lo.data_ptr() if x_lo is not None else None, int(x_is_c8), layer.cin, layer.w_t.data_ptr(),
             layer.scale.data_ptr() if affine else None, layer.bias.data_ptr() if affine else None, int(affine),
-            up_c8.data_ptr() if up_c8 is not None else None, out.data_ptr(), B, D, H, W, _stream(self.device),
+            up.hi.data_ptr() if up is not None else None, up.lo.data_ptr() if (up is not None and up.lo is not None) else None,
+            out.data_ptr(), out_lo.data_ptr() if split else None, B, D, H, W, _stream(self.device),
         )  # fmt: skip
-        _lib.check(rc, "pmnet_lateral_c96")
-        return out
+        _lib.check(rc, "pmnet_lateral_c96_split")
+        return conv.Act(out, out_lo)
 
-    def _combine(self, s_c8, u, pvec, pvox, layer: _ConvBN | None, up_c8):
+    def _combine(self, s: "conv.Act", u, pvec, pvox, layer: _ConvBN | None, up: "conv.Act | None") -> "conv.Act":
         nbox = u.shape[0]
-        _, D, H, W, _ = s_c8.shape
+        _, D, H, W, _ = s.hi.shape
+        split = s.lo is not None
         out = torch.empty((nbox, 12, D, H, W, 8), dtype=torch.bfloat16, device=self.device)
-        rc = self._L.pmnet_box_combine_c96(
-            s_c8.data_ptr(), u.data_ptr(), pvec.data_ptr(), pvox.data_ptr(),
+        out_lo = torch.empty_like(out) if split else None
+        rc = self._L.pmnet_box_combine_c96_split(
+            s.hi.data_ptr(), s.lo.data_ptr() if split else None, u.data_ptr(), pvec.data_ptr(), pvox.data_ptr(),
             layer.scale.data_ptr() if layer is not None else None, layer.bias.data_ptr() if layer is not None else None,
-            int(layer is not None), up_c8.data_ptr() if up_c8 is not None else None, out.data_ptr(),
-            nbox, D, H, W, _stream(self.device),
+            int(layer is not None), up.hi.data_ptr() if up is not None else None,
+            up.lo.data_ptr() if (up is not None and up.lo is not None) else None, out.data_ptr(),
+            out_lo.data_ptr() if split else None, nbox, D, H, W, _stream(self.device),
         )  # fmt: skip
-        _lib.check(rc, "pmnet_box_combine_c96")
-        return out
+        _lib.check(rc, "pmnet_box_combine_c96_split")
+        return conv.Act(out, out_lo)
 
     # ------------------------------------------------------------------ detector.py:36-43
     @torch.no_grad()
@@ -130,9 +153,17 @@ class PharmacoNetModel:
         bottom_up = [image, *self.backbone.forward(image)]
         # FPNDecoder.forward (decoders/fpn_decoder.py:86-115), top (4^3) to bottom (64^3)
         top = self.fpn_convs[4][0]
-        y = F.conv3d(bottom_up[4], top.weight, padding=1)  # 768 -> 96 at 4^3: 0.25 GFLOP, left to cuDNN
+        # 768 -> 96, k = 3 at 4^3 (0.25 GFLOP): im2col + one fp32 GEMM (a cuDNN fp32 convolution would silently run on
+        # TF32 tensor cores and put 1e-3 of relative error into every level below)
+        x4 = bottom_up[4]
+        B4, C4, D4 = x4.shape[0], x4.shape[1], x4.shape[2]
+        cols = F.pad(x4, (1, 1, 1, 1, 1, 1)).unfold(2, 3, 1).unfold(3, 3, 1).unfold(4, 3, 1)  # [B, C, D, H, W, 3, 3, 3]
+        cols = cols.permute(0, 2, 3, 4, 1, 5, 6, 7).reshape(B4 * D4**3, C4 * 27)
+        if not hasattr(top, "w2d"):
+            top.w2d = top.weight.reshape(96, -1).float().contiguous()
+        y = (cols @ top.w2d.t()).view(B4, D4, D4, D4, 96).permute(0, 4, 1, 2, 3)
         y = torch.relu(y * top.scale.view(1, -1, 1, 1, 1) + top.bias.view(1, -1, 1, 1, 1))
-        fpn = self._k3(conv.to_c8(y), self.fpn_convs[4][1])[0]
+        fpn = self._k3(conv.to_act(y, self.split), self.fpn_convs[4][1])[0]
         outs = [fpn]
         for level in (3, 2, 1, 0):
             fpn = self._lateral(bottom_up[level], False, self.fpn_lateral[level], fpn)
@@ -145,21 +176,23 @@ class PharmacoNetModel:
             return feats
         full = []
         for o in outs:
-            t = conv.from_c8(o)
+            t = o.float_ncdhw()
             t._pm_c8 = o  # the bf16 chunked twin travels with the tensor: later stages skip the conversion
             full.append(t)
         feats = Features(full)
         feats.c8 = outs
         return feats
 
-    def _as_c8(self, t: torch.Tensor) -> torch.Tensor:
-        """NCDHW feature tensor -> bf16 c8 (free when the tensor came out of forward_feature)."""
+    def _as_c8(self, t) -> "conv.Act":
+        """NCDHW feature tensor -> conv.Act (free when the tensor came out of forward_feature)."""
+        if isinstance(t, conv.Act):
+            return t
         twin = getattr(t, "_pm_c8", None)
         if twin is not None:
             return twin
         if t.dim() == 6:
-            return t
-        return conv.to_c8(t.to(self.device))
+            return conv.Act(t)
+        return conv.to_act(t.to(self.device), self.split)
 
     # ------------------------------------------------------------------ detector.py:45-53, cavity_head.py:45-60
     @torch.no_grad()
@@ -188,7 +221,9 @@ class PharmacoNetModel:
         # all pockets' tokens through the MLPs at once (the reference loops over images, token_head.py:62-66)
         allt = torch.cat(toks, 0)
         bidx = torch.repeat_interleave(torch.arange(len(toks), device=self.device), torch.tensor(counts, device=self.device))
-        voxel = x[bidx, :, allt[:, 0], allt[:, 1], allt[:, 2], :].reshape(-1, 96).float()
+        voxel = x.hi[bidx, :, allt[:, 0], allt[:, 1], allt[:, 2], :].reshape(-1, 96).float()
+        if x.lo is not None:
+            voxel = voxel + x.lo[bidx, :, allt[:, 0], allt[:, 1], allt[:, 2], :].reshape(-1, 96).float()
         h0 = torch.cat([voxel, sd["token_head.interaction_embedding.weight"][allt[:, 3]]], dim=1)
         skip = F.linear(h0, sd["token_head.skip.weight"], sd["token_head.skip.bias"]) if "token_head.skip.weight" in sd else h0
         h = h0
@@ -215,7 +250,9 @@ class PharmacoNetModel:
             per_level = []
             for level in range(5):  # bottom-up level = 4 - top-down index
                 f = self._as_c8(features[4 - level])[b : b + 1]
-                per_level.append(f[0] if level == 4 else self._lateral(f, True, self.mask_lateral[level], None, affine=False)[0])
+                per_level.append(
+                    f[0] if level == 4 else self._lateral(f, True, self.mask_lateral[level], None, affine=False, split=f.lo is not None)[0]
+                )
             cache[b] = per_level
         return cache[b]
 
@@ -235,7 +272,7 @@ class PharmacoNetModel:
         for b, (tokens, tfeat) in enumerate(zip(box_tokens_list, box_token_features_list)):
             tokens = tokens.to(self.device, torch.long)
             nbox = tokens.shape[0]
-            size = multi_scale_features[4].shape[2]
+            size = self._as_c8(multi_scale_features[4]).shape[2]
             if nbox == 0:
                 out_masks.append(torch.empty((0, size, size, size), dtype=torch.float32, device=self.device))
                 continue

@@ -64,6 +64,10 @@ struct Params {
   const float* head_w;    // optional fused 1x1 conv to one channel (cavity logits), fp32 [96]
   float head_b;
   float* head_out;        // [B][D][H][W] fp32
+  // split-precision passes (x = x_hi + x_lo, w = w_hi + w_lo; y = x_hi w_hi + x_lo w_hi + x_hi w_lo as three launches):
+  const float* acc_in;    // fp32 [B][D][H][W][96] partial sums of the earlier passes, added to the accumulator; or null
+  float* acc_out;         // not null: store the raw sum here (may alias acc_in) and skip activation / outputs
+  __nv_bfloat16* out_lo;  // optional second output, c8: bf16(y - float(bf16(y))), the low part of the activation
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -318,10 +322,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_k3_c96_kernel(const __grid
           const int d = d0 + g;
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (buf * 2 + g) * 128;
           float head = 0.0f;
+          const size_t vox96 = ((((size_t)it.b * p.D + d) * p.H + h) * p.W + w) * kC;  // fp32 partial-sum layout
 #pragma unroll 1
           for (int c32 = 0; c32 < 3; ++c32) {
             uint32_t v[32];
             tmem_ld32(taddr + c32 * 32, v);
+            if (p.acc_in && inside) {
+              const float4* a4 = reinterpret_cast<const float4*>(p.acc_in + vox96 + c32 * 32);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 t = a4[q];
+                v[4 * q + 0] = __float_as_uint(__uint_as_float(v[4 * q + 0]) + t.x);
+                v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + t.y);
+                v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + t.z);
+                v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + t.w);
+              }
+            }
+            if (p.acc_out) {
+              if (inside) {
+                float4* o4 = reinterpret_cast<float4*>(p.acc_out + vox96 + c32 * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  o4[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                      __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+              }
+              continue;
+            }
             float y[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -349,10 +375,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_k3_c96_kernel(const __grid
                 pk.w = *reinterpret_cast<uint32_t*>(&b3);
                 const size_t vox = (((size_t)it.b * kChunks + chunk) * p.D + d) * plane_vox + (size_t)h * p.W + w;
                 *reinterpret_cast<uint4*>(p.out + vox * 8) = pk;
+                if (p.out_lo) {
+                  // residual of the bf16 rounding: the next layer's x_lo
+                  const float2 f0 = __bfloat1622float2(b0), f1 = __bfloat1622float2(b1), f2 = __bfloat1622float2(b2),
+                               f3 = __bfloat1622float2(b3);
+                  __nv_bfloat162 l0 = __floats2bfloat162_rn(y[q * 8 + 0] - f0.x, y[q * 8 + 1] - f0.y);
+                  __nv_bfloat162 l1 = __floats2bfloat162_rn(y[q * 8 + 2] - f1.x, y[q * 8 + 3] - f1.y);
+                  __nv_bfloat162 l2 = __floats2bfloat162_rn(y[q * 8 + 4] - f2.x, y[q * 8 + 5] - f2.y);
+                  __nv_bfloat162 l3 = __floats2bfloat162_rn(y[q * 8 + 6] - f3.x, y[q * 8 + 7] - f3.y);
+                  uint4 pl;
+                  pl.x = *reinterpret_cast<uint32_t*>(&l0);
+                  pl.y = *reinterpret_cast<uint32_t*>(&l1);
+                  pl.z = *reinterpret_cast<uint32_t*>(&l2);
+                  pl.w = *reinterpret_cast<uint32_t*>(&l3);
+                  *reinterpret_cast<uint4*>(p.out_lo + vox * 8) = pl;
+                }
               }
             }
           }
-          if (p.head_out && inside)
+          if (p.head_out && !p.acc_out && inside)
             p.head_out[((size_t)it.b * p.D + d) * plane_vox + (size_t)h * p.W + w] = head + p.head_b;
         }
         tc_fence_before();
@@ -389,13 +430,29 @@ static EncodeTiledFn get_encode() {
 
 extern void pmnet_set_error(const char* msg);
 
+extern "C" int pmnet_conv3d_k3_c96_pass(const void* x_c8, const void* w_packed, const float* scale, const float* bias,
+                                        void* y_c8, void* y_lo_c8, const float* acc_in, float* acc_out,
+                                        const float* head_w, float head_b, float* head_out, int32_t B, int32_t D,
+                                        int32_t H, int32_t W, int32_t relu, int32_t planes_per_item, int32_t max_ctas,
+                                        void* stream_);
+
 extern "C" int pmnet_conv3d_k3_c96(const void* x_c8, const void* w_packed, const float* scale, const float* bias,
                                    void* y_c8, const float* head_w, float head_b, float* head_out, int32_t B,
                                    int32_t D, int32_t H, int32_t W, int32_t relu, int32_t planes_per_item,
                                    int32_t max_ctas, void* stream_) {
+  return pmnet_conv3d_k3_c96_pass(x_c8, w_packed, scale, bias, y_c8, nullptr, nullptr, nullptr, head_w, head_b, head_out,
+                                  B, D, H, W, relu, planes_per_item, max_ctas, stream_);
+}
+
+extern "C" int pmnet_conv3d_k3_c96_pass(const void* x_c8, const void* w_packed, const float* scale, const float* bias,
+                                        void* y_c8, void* y_lo_c8, const float* acc_in, float* acc_out,
+                                        const float* head_w, float head_b, float* head_out, int32_t B, int32_t D,
+                                        int32_t H, int32_t W, int32_t relu, int32_t planes_per_item, int32_t max_ctas,
+                                        void* stream_) {
   using namespace pmconv;
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!x_c8 || !w_packed || !scale || !bias || (!y_c8 && !head_out) || (head_out && !head_w)) {
+  if (!x_c8 || !w_packed || !scale || !bias || (!y_c8 && !head_out && !acc_out) || (head_out && !head_w) ||
+      (y_lo_c8 && !y_c8)) {
     pmnet_set_error("pmnet_conv3d_k3_c96: null argument");
     return PMNET_EINVAL;
   }
@@ -436,6 +493,7 @@ extern "C" int pmnet_conv3d_k3_c96(const void* x_c8, const void* w_packed, const
   p.out = (__nv_bfloat16*)y_c8;
   p.relu = relu;
   p.head_w = head_w; p.head_b = head_b; p.head_out = head_out;
+  p.acc_in = acc_in; p.acc_out = acc_out; p.out_lo = (__nv_bfloat16*)y_lo_c8;
   int sms = 148;
   {
     int dev = 0;

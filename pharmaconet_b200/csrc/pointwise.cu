@@ -38,6 +38,26 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return p;
 }
 
+// y -> (hi, lo) with hi = bf16(y), lo = bf16(y - hi): the two-term split the convolution's extra passes consume
+__device__ __forceinline__ void pack8_split(const float (&f)[8], uint4& hi, uint4& lo) {
+  hi = pack8(f);
+  float h[8], r[8];
+  unpack8(hi, h);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = f[i] - h[i];
+  lo = pack8(r);
+}
+__device__ __forceinline__ void unpack8_sum(const uint4* __restrict__ hi, const uint4* __restrict__ lo, size_t i,
+                                            float (&f)[8]) {
+  unpack8(__ldg(hi + i), f);
+  if (lo) {
+    float g[8];
+    unpack8(__ldg(lo + i), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += g[j];
+  }
+}
+
 constexpr int kLatVox = 128;   // voxels per block tile
 constexpr int kLatTiles = 4;   // tiles per block (the weight tile is loaded once per 512 voxels)
 
@@ -49,7 +69,8 @@ template <int IN_C8>
 __global__ void __launch_bounds__(128) lateral_kernel(const void* __restrict__ x, int cin, const float* __restrict__ wt,
                                                       const float* __restrict__ scale, const float* __restrict__ bias,
                                                       int relu, const uint4* __restrict__ up, uint4* __restrict__ out,
-                                                      int D, int H, int W) {
+                                                      int D, int H, int W, const uint4* __restrict__ x_lo,
+                                                      const uint4* __restrict__ up_lo, uint4* __restrict__ out_lo) {
   extern __shared__ __align__(16) float sw[];  // [cin][96]
   const int V = D * H * W;
   for (int i = threadIdx.x; i < cin * 96; i += blockDim.x) sw[i] = wt[i];
@@ -73,7 +94,7 @@ __global__ void __launch_bounds__(128) lateral_kernel(const void* __restrict__ x
         for (int i = 0; i < 4; ++i) {
           const int v = v0 + lane + 32 * i;
           if (v < V) {
-            unpack8(__ldg(xp + (size_t)q * V + v), f[i]);
+            unpack8_sum(xp, x_lo ? x_lo + (size_t)b * (cin / 8) * V : nullptr, (size_t)q * V + v, f[i]);
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[i][j] = 0.0f;
@@ -145,11 +166,18 @@ __global__ void __launch_bounds__(128) lateral_kernel(const void* __restrict__ x
         }
         if (up) {
           float u[8];
-          unpack8(__ldg(up + ((size_t)b * 12 + chunk) * Vu + vu), u);
+          unpack8_sum(up, up_lo, ((size_t)b * 12 + chunk) * Vu + vu, u);
 #pragma unroll
           for (int j = 0; j < 8; ++j) y[j] += u[j];
         }
-        out[((size_t)b * 12 + chunk) * V + v] = pack8(y);
+        if (out_lo) {
+          uint4 ph, pl;
+          pack8_split(y, ph, pl);
+          out[((size_t)b * 12 + chunk) * V + v] = ph;
+          out_lo[((size_t)b * 12 + chunk) * V + v] = pl;
+        } else {
+          out[((size_t)b * 12 + chunk) * V + v] = pack8(y);
+        }
       }
     }
   }
@@ -163,13 +191,14 @@ __global__ void __launch_bounds__(256) box_combine_kernel(const uint4* __restric
                                                           const float* __restrict__ scale,
                                                           const float* __restrict__ bias, int relu,
                                                           const uint4* __restrict__ up, uint4* __restrict__ out,
-                                                          int nbox, int D, int H, int W) {
+                                                          int nbox, int D, int H, int W, const uint4* __restrict__ S_lo,
+                                                          const uint4* __restrict__ up_lo, uint4* __restrict__ out_lo) {
   const int V = D * H * W;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // chunk * V + v
   if (idx >= (size_t)12 * V) return;
   const int chunk = (int)(idx / V), v = (int)(idx % V);
   float s[8];
-  unpack8(__ldg(S + idx), s);
+  unpack8_sum(S, S_lo, idx, s);
   float sc[8], bi[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -194,11 +223,18 @@ __global__ void __launch_bounds__(256) box_combine_kernel(const uint4* __restric
     }
     if (up) {
       float uu[8];
-      unpack8(__ldg(up + ((size_t)j * 12 + chunk) * Vu + vu), uu);
+      unpack8_sum(up, up_lo, ((size_t)j * 12 + chunk) * Vu + vu, uu);
 #pragma unroll
       for (int k = 0; k < 8; ++k) y[k] += uu[k];
     }
-    out[((size_t)j * 12 + chunk) * V + v] = pack8(y);
+    if (out_lo) {
+      uint4 ph, pl;
+      pack8_split(y, ph, pl);
+      out[((size_t)j * 12 + chunk) * V + v] = ph;
+      out_lo[((size_t)j * 12 + chunk) * V + v] = pl;
+    } else {
+      out[((size_t)j * 12 + chunk) * V + v] = pack8(y);
+    }
   }
 }
 
@@ -260,7 +296,18 @@ extern "C" {
 int pmnet_lateral_c96(const void* x, int32_t x_is_c8, int32_t c_in, const float* w_t, const float* scale,
                       const float* bias, int32_t relu, const void* up_c8, void* out_c8, int32_t B, int32_t D,
                       int32_t H, int32_t W, void* stream_) {
+  return pmnet_lateral_c96_split(x, nullptr, x_is_c8, c_in, w_t, scale, bias, relu, up_c8, nullptr, out_c8, nullptr, B, D, H,
+                                 W, stream_);
+}
+
+int pmnet_lateral_c96_split(const void* x, const void* x_lo, int32_t x_is_c8, int32_t c_in, const float* w_t,
+                            const float* scale, const float* bias, int32_t relu, const void* up_c8, const void* up_lo_c8,
+                            void* out_c8, void* out_lo_c8, int32_t B, int32_t D, int32_t H, int32_t W, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if ((x_lo && !x_is_c8) || (up_lo_c8 && !up_c8)) {
+    pmnet_set_error("pmnet_lateral_c96_split: a low part needs its high part in c8 layout");
+    return PMNET_EINVAL;
+  }
   if (!x || !w_t || !out_c8 || (scale && !bias)) {
     pmnet_set_error("pmnet_lateral_c96: null argument");
     return PMNET_EINVAL;
@@ -281,12 +328,13 @@ int pmnet_lateral_c96(const void* x, int32_t x_is_c8, int32_t c_in, const float*
     e = cudaFuncSetAttribute(lateral_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       lateral_kernel<1><<<grid, 128, smem, stream>>>(x, c_in, w_t, scale, bias, relu, (const uint4*)up_c8, (uint4*)out_c8,
-                                                     D, H, W);
+                                                     D, H, W, (const uint4*)x_lo, (const uint4*)up_lo_c8,
+                                                     (uint4*)out_lo_c8);
   } else {
     e = cudaFuncSetAttribute(lateral_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       lateral_kernel<0><<<grid, 128, smem, stream>>>(x, c_in, w_t, scale, bias, relu, (const uint4*)up_c8, (uint4*)out_c8,
-                                                     D, H, W);
+                                                     D, H, W, nullptr, (const uint4*)up_lo_c8, (uint4*)out_lo_c8);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -299,6 +347,14 @@ int pmnet_lateral_c96(const void* x, int32_t x_is_c8, int32_t c_in, const float*
 int pmnet_box_combine_c96(const void* s_c8, const float* u, const float* pvec, const int32_t* pvox,
                           const float* scale, const float* bias, int32_t relu, const void* up_c8, void* out_c8,
                           int32_t nbox, int32_t D, int32_t H, int32_t W, void* stream_) {
+  return pmnet_box_combine_c96_split(s_c8, nullptr, u, pvec, pvox, scale, bias, relu, up_c8, nullptr, out_c8, nullptr, nbox,
+                                     D, H, W, stream_);
+}
+
+int pmnet_box_combine_c96_split(const void* s_c8, const void* s_lo_c8, const float* u, const float* pvec,
+                                const int32_t* pvox, const float* scale, const float* bias, int32_t relu,
+                                const void* up_c8, const void* up_lo_c8, void* out_c8, void* out_lo_c8, int32_t nbox,
+                                int32_t D, int32_t H, int32_t W, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!s_c8 || !u || !out_c8 || !pvec || !pvox || (scale && !bias)) {
     pmnet_set_error("pmnet_box_combine_c96: null argument");
@@ -311,7 +367,7 @@ int pmnet_box_combine_c96(const void* s_c8, const float* u, const float* pvec, c
   const size_t total = (size_t)12 * D * H * W;
   box_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
       (const uint4*)s_c8, u, pvec, (const int4*)pvox, scale, bias, relu, (const uint4*)up_c8, (uint4*)out_c8, nbox, D, H,
-      W);
+      W, (const uint4*)s_lo_c8, (const uint4*)up_lo_c8, (uint4*)out_lo_c8);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     pmnet_set_error(cudaGetErrorString(e));

@@ -2,7 +2,7 @@
 // namespace). Same algorithm, same fp32 operations in the same order and therefore bit-identical results as
 // pmnet_score_kernel (the generic kernel, which stays the in-launch fallback), restricted to
 //   up to 32 conformers (lane = conformer), model tables pinned in shared memory,
-//   per ligand: <= 96 (level, model cluster) entries, <= 32 entries per level, <= 12 levels, <= 224 node-match records
+//   per ligand: <= 88 (level, model cluster) entries, <= 32 entries per level, <= 12 levels, <= 224 node-match records
 //   with <= 3 matched model nodes each, <= 48 ligand nodes in the levels, <= 384 mask-stack words, <= 4096 pair
 //   entries and <= 2048 pair-score rows.
 // A ligand outside these caps gets status PMNET_LIG_DEFERRED and is scored by the generic kernel, which
@@ -25,7 +25,7 @@
 
 namespace fastk {
 
-constexpr int TC = 96;      // (level, model cluster) entries per ligand
+constexpr int TC = 88;      // (level, model cluster) entries per ligand (88: keeps the CTA under the 164 KB carve-out)
 constexpr int RC = 224;     // node-match records per ligand
 constexpr int LC = 12;      // levels
 constexpr int NLC = 48;     // ligand nodes in the selected levels
@@ -153,13 +153,21 @@ __device__ __forceinline__ int leaf_pass(const WarpS& ws, const float* __restric
                                          const int base, const unsigned lmw, unsigned bal, const float tt,
                                          const bool is_anc, const int pb, const int dmax, const int lane, float& best) {
   int nleaf = 0;
+  // the row indices of the next leaf are requested while the current one is summed (two dependent loads per leaf)
+  int nf = base + __ffs(bal) - 1;
+  int myrow_n = (is_anc && bal) ? prow[pb + nf] : -1;
+  unsigned sr_n = bal ? ws.srow[nf] : 0xffffu;
   while (bal) {
     const int src = __ffs(bal) - 1;
     bal &= bal - 1;
-    const int leaf = base + src;
-    const int myrow = is_anc ? prow[pb + leaf] : -1;
-    const unsigned sr = ws.srow[leaf];
+    const int myrow = myrow_n;
+    const unsigned sr = sr_n;
     const float self = (sr != 0xffffu) ? rows_l[sr * 32u] : 0.0f;
+    if (bal) {
+      nf = base + __ffs(bal) - 1;
+      myrow_n = is_anc ? prow[pb + nf] : -1;
+      sr_n = ws.srow[nf];
+    }
     float t = 0.0f;
     for (int a0 = 1; a0 <= dmax; a0 += 2) {  // two independent row loads per round (lanes > dmax hold -1)
       const int r0 = __shfl_sync(kFull, myrow, a0), r1 = __shfl_sync(kFull, myrow, a0 + 1);
@@ -546,6 +554,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) pmnet_score_fast_kernel(const 
           int d = 0, slot = 0, nmatch = 0, entry = -1, maxm = 0, phase = 0;
           unsigned alive = cfull;
           int my_pbase = kNoBase;
+          int pf_found = -1, pf_row = -1;  // prefetched row indices of the next sibling (lane a: ancestor at depth a)
           unsigned cand = (ws.lev_start[1] >= 32) ? kFull : ((1u << ws.lev_start[1]) - 1u);  // every entry of level 0
           bool hadc = true;
           for (;;) {
@@ -577,7 +586,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) pmnet_score_fast_kernel(const 
               const int found = ws.lev_start[y] + src;
               const unsigned alive2 = pm[found];
               ++st_nodes;
-              const int myrow = is_anc ? prow[my_pbase + found] : -1;
+              const int myrow = (pf_found == found) ? pf_row : (is_anc ? prow[my_pbase + found] : -1);
+              // the next sibling's row indices are requested now (used unless this child is pushed in between)
+              pf_found = -1;
+              if (cand) {
+                pf_found = ws.lev_start[y] + __ffs(cand) - 1;
+                pf_row = is_anc ? prow[my_pbase + pf_found] : -1;
+              }
               const unsigned sr = ws.srow[found];
               const int pbc = ws.rowbase[found];
               // the child's candidate masks: parent mask & conformers alive in the child & pair validity
@@ -638,6 +653,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) pmnet_score_fast_kernel(const 
                                            ((uint32_t)slot << 24) | (hadc ? (1u << 30) : 0u) | ((uint32_t)phase << 31),
                                        0u);
               if (lane == d + 1) my_pbase = pbc;
+              pf_found = -1;
               const int width = ws.lev_start[y + 2] - end;
               cand = balc & (width >= 32 ? kFull : ((1u << width) - 1u));
               hadc = cand != 0u;
@@ -658,6 +674,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) pmnet_score_fast_kernel(const 
                                            ((uint32_t)slot << 24) | (hadc ? (1u << 30) : 0u) | (1u << 31),
                                        0u);
               if (lane == d + 1) my_pbase = kNoBase;
+              pf_found = -1;
               d += 1;
               entry = -1;
               maxm = 0;

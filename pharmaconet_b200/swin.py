@@ -61,6 +61,12 @@ class SwinV2Backbone:
         return F.linear(x, self._g(wname), bias)
 
     def _g(self, name: str) -> torch.Tensor:
+        if name.endswith("#2d"):  # a convolution weight viewed as the [C_out, C_in * k^3] matrix of its GEMM form
+            t = self._scale_cache.get(name)
+            if t is None:
+                w = self.sd[self.p + name[:-3]]
+                t = self._scale_cache[name] = w.reshape(w.shape[0], -1).contiguous()
+            return t
         return self.sd[self.p + name]
 
     def _rel_bias(self, blk: str, heads: int, n: int) -> torch.Tensor:
@@ -183,9 +189,14 @@ class SwinV2Backbone:
     @torch.no_grad()
     def forward(self, image: torch.Tensor) -> list[torch.Tensor]:
         """image fp32 [B, 33, 64, 64, 64] -> [B,96,32^3], [B,192,16^3], [B,384,8^3], [B,768,4^3] (NCDHW fp32)."""
-        x = F.conv3d(image, self._g("patch_embed.proj.weight"), self._g("patch_embed.proj.bias"), stride=PATCH)
-        B, C = x.shape[0], x.shape[1]
-        x = x.flatten(2).transpose(1, 2)
+        # PatchEmbed (swinv2.py:484-500): the k = 2, stride = 2 convolution is a GEMM over non-overlapping 2^3 patches
+        # (K = 33 * 8 = 264). Written as one: cuDNN would run an fp32 convolution on TF32 tensor cores by default.
+        B, Cin, D, H, W = image.shape
+        w = self._g("patch_embed.proj.weight")
+        C = w.shape[0]
+        patches = image.view(B, Cin, D // PATCH, PATCH, H // PATCH, PATCH, W // PATCH, PATCH)
+        patches = patches.permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(B, -1, Cin * PATCH**3)
+        x = self._lin(patches, "patch_embed.proj.weight#2d", self._g("patch_embed.proj.bias"))
         if self.fused and x.is_cuda:
             x = self._ln_res(None, x.contiguous(), "patch_embed.norm.weight", "patch_embed.norm.bias")
         else:

@@ -28,7 +28,19 @@ def setup():
     tokens = torch.cat([torch.randint(0, 64, (200, 3), generator=g), torch.randint(0, 10, (200, 1), generator=g)], dim=1)
     assert np.array_equal(tokens.numpy(), gold["tokens"])
     feats = model.forward_feature(image.cuda())
-    return dict(model=model, gold=gold, image=image, tokens=tokens.long(), feats=feats)
+    model.precision = "bf16x3"  # the split-precision mode: two-term bf16 operands, three tensor-core passes per conv
+    feats_x3 = model.forward_feature(image.cuda())
+    model.precision = "bf16"
+    return dict(model=model, gold=gold, image=image, tokens=tokens.long(), feats=feats, feats_x3=feats_x3)
+
+
+def _flips(gold, key, mine_bits):
+    """(number of mask voxels that differ from the fp32 CPU reference, how many of them lie outside the recorded band
+    |reference logit| < 5e-3 around the threshold)"""
+    bits = np.unpackbits(gold[f"{key}_bits"]).astype(bool)
+    diff = np.nonzero(bits != mine_bits)[0]
+    outside = np.setdiff1d(diff, gold[f"{key}_near_idx"])
+    return len(diff), len(outside), bits.size
 
 
 def _sample(t, n):
@@ -71,6 +83,57 @@ def test_cavity_masks(setup):
         # sigmoid(x) > 0.5 <=> x > 0 (module.py:232-233); voxels whose fp32 logit is within bf16 noise of 0 may flip
         assert flips <= 0.003 * bits.size, (name, flips)
         print(f"cavity {name}: {flips} of {bits.size} mask voxels differ from the fp32 reference")
+
+
+def test_split_precision_features(setup):
+    """bf16x3: the multi-scale features agree with the fp32 reference to the fp16 resolution of the stored samples."""
+    for i, f in enumerate(setup["feats_x3"]):
+        ref = setup["gold"][f"feat{i}"].astype(np.float32)
+        mine = _sample(f, 8)
+        rel_rms = np.sqrt(np.mean((mine - ref) ** 2)) / np.sqrt(np.mean(ref**2))
+        assert rel_rms <= 6e-4, (i, rel_rms)  # the golden samples are fp16 (2^-11 relative)
+
+
+def test_cavity_masks_split_precision(setup):
+    """module.py:232-233: sigmoid(logit) > 0.5 <=> logit > 0. In the split-precision mode the integer masks equal the
+    fp32 CPU reference except, at most, for voxels whose reference logit lies within fp32 reordering noise of 0."""
+    model = setup["model"]
+    model.precision = "bf16x3"
+    try:
+        narrow, wide = model.forward_cavity_extraction(setup["feats_x3"][-1])
+    finally:
+        model.precision = "bf16"
+    for name, t in (("narrow", narrow), ("wide", wide)):
+        ref16 = setup["gold"][f"cavity_{name}_f16_s4"].astype(np.float32)
+        mine = t[0, 0, ::4, ::4, ::4].cpu().numpy()
+        assert np.abs(mine - ref16).max() <= 2e-3 * max(1.0, np.abs(ref16).max())  # fp16 storage of the golden samples
+        near_val = setup["gold"][f"cavity_{name}_near_val"]
+        mine_near = t[0, 0].reshape(-1)[torch.from_numpy(setup["gold"][f"cavity_{name}_near_idx"]).long().cuda()].cpu().numpy()
+        err = float(np.abs(mine_near - near_val).max())
+        n, outside, total = _flips(setup["gold"], f"cavity_{name}", (t[0, 0] > 0).reshape(-1).cpu().numpy())
+        print(f"cavity {name} (bf16x3): {n} of {total} mask voxels differ; logit error on the near-threshold voxels {err:.2e}")
+        assert outside == 0 and n <= 2, (name, n, outside)
+        assert err <= 2e-4
+
+
+def test_segmentation_split_precision(setup):
+    model, gold = setup["model"], setup["gold"]
+    model.precision = "bf16x3"
+    try:
+        _, tfeat = model.forward_token_prediction(setup["feats_x3"][-1], [setup["tokens"]])
+        hot = setup["tokens"][:4]
+        seg = model.forward_segmentation(setup["feats_x3"], [hot], [tfeat[0][:4]])[0][0]
+    finally:
+        model.precision = "bf16"
+    ref_s, ref_f = gold["token_scores"], gold["token_features"]
+    assert np.abs(tfeat[0].cpu().numpy() - ref_f).max() <= 2e-4 * max(1.0, np.abs(ref_f).max())
+    mine_near = seg.reshape(-1)[torch.from_numpy(gold["seg_near_idx"]).long().cuda()].cpu().numpy()
+    err = float(np.abs(mine_near - gold["seg_near_val"]).max())
+    n, outside, total = _flips(gold, "seg", (seg > 0).reshape(-1).cpu().numpy())
+    print(f"segmentation (bf16x3): {n} of {total} mask voxels differ; logit error on the near-threshold voxels {err:.2e} "
+          f"(logit rms {float(gold['seg_rms']):.1f})")
+    assert outside == 0 and n <= 4, (n, outside)
+    assert err <= 1e-3
 
 
 def test_token_prediction(setup):
@@ -122,7 +185,7 @@ def test_modeling_pipeline_against_reference_pharmaconet():
     gold = np.load(os.path.join(GOLDEN, "cnn_pipeline_golden.npz"))
     man = json.load(open(os.path.join(GOLDEN, "cnn_manifest.json")))
     buf = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, "cnn_buffers.npz")).items()}
-    net = PharmacoNet("cuda:0", verbose=False, checkpoint=cnn_weights.synth_checkpoint(man, buf, 0))
+    net = PharmacoNet("cuda:0", verbose=False, checkpoint=cnn_weights.synth_checkpoint(man, buf, 0), precision="bf16")
     g = torch.Generator().manual_seed(0)
     image = torch.rand((33, 64, 64, 64), generator=g)
     gm = torch.Generator().manual_seed(2)
@@ -160,6 +223,43 @@ def test_modeling_pipeline_against_reference_pharmaconet():
 
     scores = model.scoring_batch(LigandBatch.from_typed(synthetic.make_ligands(64, 8, seed=5)), device="cuda:0")
     assert scores.shape == (64,) and np.all(np.isfinite(scores))
+
+
+def _selected(net, infos, tokens, token_pos):
+    sel = []
+    for info in infos:
+        d = (token_pos - torch.as_tensor(info["hotspot_position"]).float()).abs().sum(1)
+        cand = torch.nonzero(d < 1e-6).reshape(-1).tolist()
+        sel.append([c for c in cand if net_type(tokens[c, 3]) == info["nci_type"]][0])
+    return sel
+
+
+def test_modeling_pipeline_split_precision_selects_the_reference_hotspots_exactly():
+    """The default (split-precision) PharmacoNet against the reference's own module.py run on CPU: the selected hotspot
+    INDICES (module.py:235-253, an integer output) are identical, the density maps have the reference's support size
+    to within the voxels that sit on the 0.5 threshold, the relative scores agree to 1e-3."""
+    from pharmaconet_b200.module import PharmacoNet
+
+    gold = np.load(os.path.join(GOLDEN, "cnn_pipeline_golden.npz"))
+    man = json.load(open(os.path.join(GOLDEN, "cnn_manifest.json")))
+    buf = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, "cnn_buffers.npz")).items()}
+    net = PharmacoNet("cuda:0", verbose=False, checkpoint=cnn_weights.synth_checkpoint(man, buf, 0))
+    assert net.precision == "bf16x3"
+    image = torch.rand((33, 64, 64, 64), generator=torch.Generator().manual_seed(0))
+    mask = torch.rand((64, 64, 64), generator=torch.Generator().manual_seed(2)) < 0.8
+    tokens = torch.from_numpy(gold["tokens"]).long()
+    token_pos = (tokens[:, :3].float() - 31.5) * 0.5
+    infos = net.create_density_maps((image, mask, token_pos, tokens))
+    sel = _selected(net, infos, tokens, token_pos)
+    ref_sel = gold["selected_with_nonempty_map"].tolist()
+    assert sel == ref_sel
+    nz = np.asarray([int((i["point_map"] > 0).sum()) for i in infos])
+    rel = np.abs(nz - gold["map_nonzero"]) / np.maximum(gold["map_nonzero"], 1)
+    print(f"hotspots {len(sel)} identical; density-map support sizes: max rel diff {rel.max():.2e}, exact {int((nz == gold['map_nonzero']).sum())}/{len(nz)}")
+    assert rel.max() <= 5e-3
+    assert np.abs(np.asarray([i["hotspot_score"] for i in infos]) - gold["rel_scores"]).max() <= 1e-3
+    model = net.create_model((image, mask, token_pos, tokens))
+    assert len(model.nodes) == int(gold["model_nodes"]) and len(model.node_clusters) == int(gold["model_clusters"])
 
 
 def net_type(t):
