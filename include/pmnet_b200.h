@@ -247,6 +247,28 @@ int pmnet_window_attention(const void* qkv, void* out, const float* logit_scale,
 int pmnet_ln_residual(const float* shortcut, const void* h, int32_t h_is_bf16, const float* gamma, const float* beta,
                       float* y, int64_t rows, int32_t C, float eps, void* stream);
 
+/* Same two kernels emitting the two-term bf16 split of their result (hi = bf16(y), lo = bf16(y - hi)), the operand
+ * pair of a split-precision pmnet_gemm_bf16: the attention result [B * res^3][heads * 32] from fp32 qkv, and the
+ * LayerNorm output (fp32 y as before, plus y_hi and optionally y_lo, [rows][C]). */
+int pmnet_window_attention_split(const float* qkv, void* out_hi, void* out_lo, const float* logit_scale,
+                                 const float* rel_bias, const float* attn_mask, int32_t B, int32_t res, int32_t shift,
+                                 int32_t heads, void* stream);
+int pmnet_ln_residual_split(const float* shortcut, const void* h, int32_t h_is_bf16, const float* gamma,
+                            const float* beta, float* y, void* y_hi, void* y_lo, int64_t rows, int32_t C, float eps,
+                            void* stream);
+
+/* Linear layer y[M][N] = act(a[M][K] . w[N][K]^T + bias) on tcgen05 (csrc/gemm.cu): nn.Linear of the Swin blocks
+ * (swinv2.py:114-158, swin.py:19-44), PatchMerging.reduction (swinv2.py:346-363), PatchEmbed.proj and the 4^3 FPN
+ * convolution in im2col form, the 1x1 laterals of the small FPN levels, the token- and mask-head MLPs.
+ *   a_hi, w_hi : bf16 row-major, K contiguous, 16-byte aligned; K % 8 == 0; N <= 96 or N % 96 == 0, N % 32 == 0
+ *   a_lo, w_lo : both NULL = one tensor-core pass over bf16 operands; both given = the two-term split operands
+ *                (value = hi + lo) and three passes hi.hi + lo.hi + hi.lo into one fp32 accumulator
+ *   bias       : fp32 [N] or NULL;  act: 0 none, 1 GELU (erf), 2 ReLU, 3 SiLU
+ *   out_f32    : fp32 [M][N] or NULL; out_hi / out_lo : bf16 [M][N] or NULL, the split of the result */
+int pmnet_gemm_bf16(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                    float* out_f32, void* out_hi, void* out_lo, int64_t M, int32_t N, int32_t K, int32_t act,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

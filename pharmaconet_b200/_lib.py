@@ -13,7 +13,7 @@ from . import _abi
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("PMNET_B200_SO") or os.path.join(_PKG, "libpmnet_b200.so")  # env override: developer A/B builds
-SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("scoring.cu", "conv3d.cu", "pointwise.cu", "swin_ops.cu")]
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("scoring.cu", "conv3d.cu", "pointwise.cu", "swin_ops.cu", "gemm.cu")]
 HEADERS = [os.path.join(_ROOT, "include", "pmnet_b200.h"), os.path.join(_PKG, "csrc", "scoring_fast.cuh")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -143,6 +143,21 @@ def lib() -> C.CDLL:
         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,
         C.c_void_p,
     ]  # fmt: skip
+    L.pmnet_window_attention_split.restype = C.c_int
+    L.pmnet_window_attention_split.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+        C.c_int32, C.c_void_p,
+    ]  # fmt: skip
+    L.pmnet_ln_residual_split.restype = C.c_int
+    L.pmnet_ln_residual_split.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+        C.c_int32, C.c_float, C.c_void_p,
+    ]  # fmt: skip
+    L.pmnet_gemm_bf16.restype = C.c_int
+    L.pmnet_gemm_bf16.argtypes = [
+        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+        C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+    ]  # fmt: skip
     _lib = L
     return L
 
@@ -170,5 +185,8 @@ EXPORTS = (
     "pmnet_box_combine_c96_split",
     "pmnet_density_post",
     "pmnet_window_attention",
+    "pmnet_window_attention_split",
     "pmnet_ln_residual",
+    "pmnet_ln_residual_split",
+    "pmnet_gemm_bf16",
 )

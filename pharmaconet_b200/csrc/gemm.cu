@@ -1,0 +1,329 @@
+// gemm.cu - C[M, N] = act(A[M, K] . W[N, K]^T + bias) on the sm_100a tensor cores (tcgen05 + TMEM + TMA), the linear
+// layers of the reference network that are not 3x3x3 convolutions:
+//   WindowAttention.qkv / .proj, Mlp.fc1 / .fc2          src/pmnet/network/backbones/swinv2.py:114-158, swin.py:19-44
+//   PatchMerging.reduction, PatchEmbed.proj (as a GEMM)    swinv2.py:346-363, 484-500
+//   FPNDecoder top-level conv (im2col) and small laterals  decoders/fpn_decoder.py:86-115
+//   TokenHead / MaskHead MLPs                               token_head.py:50-86, mask_head.py:128-168
+//
+// Operands are bf16, K-major (row-major with K contiguous), fetched by TMA as 64-element (128 B) wide boxes with the
+// 128-byte swizzle; accumulation is fp32 in TMEM. One CTA computes one 128 x BN output tile (BN = 96 or 192: every
+// layer width of the network is a multiple of 96) through a 4-stage TMA -> tcgen05.mma pipeline:
+//   warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-5 = epilogue (TMEM -> registers -> bias / GELU ->
+//   fp32 and / or bf16 stores; TMEM lane quadrant = warp % 4).
+// Split precision: with a_lo / w_lo given the K loop runs three times over (a_hi, w_hi), (a_lo, w_hi), (a_hi, w_lo) into
+// the SAME accumulator - x w = x_hi w_hi + x_lo w_hi + x_hi w_lo to 2^-16 relative - and the epilogue can emit the
+// (hi, lo) pair of its result for the next layer. Out-of-range rows / columns / K tails are zero-filled by TMA.
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pmnet_b200.h"
+
+extern void pmnet_set_error(const char* msg);
+
+namespace pmgemm {
+
+constexpr int BM = 128, BK = 64, kStages = 4;
+constexpr int kThreads = 192;
+constexpr int kABytes = BM * BK * 2;  // 16384
+
+struct Params {
+  int M, N, K;
+  int npass;
+  int pa[3], pb[3];        // operand index (0 = hi, 1 = lo) of A and W in each pass
+  const float* bias;       // [N] or null
+  float* out_f32;          // [M][N] or null
+  __nv_bfloat16* out_hi;   // [M][N] or null: bf16(y)
+  __nv_bfloat16* out_lo;   // [M][N] or null: bf16(y - bf16(y))
+  int act;                 // 0 none, 1 GELU (erf), 2 ReLU, 3 SiLU
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.b32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(addr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory matrix descriptor for a tile of 128-byte rows written by TMA with CU_TENSOR_MAP_SWIZZLE_128B
+// (cute::UMMA::SmemDescriptor): start >> 4, leading byte offset (unused for swizzled K-major layouts, 1), stride byte
+// offset = 8 rows x 128 B = 1024, version 1, layout type 2 = SWIZZLE_128B. A K step of 16 elements moves the start by 32 B.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == 1) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));  // nn.GELU (swin.py:32)
+  if (act == 2) return fmaxf(x, 0.0f);
+  if (act == 3) return x / (1.0f + __expf(-x));
+  return x;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                           const __grid_constant__ CUtensorMap tmA1,
+                                                           const __grid_constant__ CUtensorMap tmB0,
+                                                           const __grid_constant__ CUtensorMap tmB1, const Params p) {
+  constexpr int kBBytes = BN * BK * 2;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = BN <= 128 ? 128 : 256;
+  // instruction descriptor, kind::f16: D = f32 (bit 4), A = B = bf16 (bits 7, 10), K-major, N >> 3 at 17, M >> 4 at 24
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // the swizzled tiles need 1024-byte alignment in the shared window: align explicitly (1 KB of slack is allocated)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + kStages * kStageBytes;  // full[4], empty[4], accfull
+  auto bar_full = [&](int s) { return bars + 8u * s; };
+  auto bar_empty = [&](int s) { return bars + 8u * (kStages + s); };
+  const uint32_t bar_acc = bars + 8u * (2 * kStages);
+  volatile uint32_t* tmem_ptr_smem = (volatile uint32_t*)(smem + kStages * kStageBytes + 8 * (2 * kStages + 1));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kblocks = (p.K + BK - 1) / BK;
+  const int total = kblocks * p.npass;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((void*)tmem_ptr_smem)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < total; ++it) {
+        const int pass = it / kblocks, kb = it - pass * kblocks;
+        const int s = it % kStages, round = it / kStages;
+        mbar_wait(bar_empty(s), (round & 1) ^ 1);
+        mbar_expect_tx(bar_full(s), kStageBytes);
+        const CUtensorMap* ma = p.pa[pass] ? &tmA1 : &tmA0;
+        const CUtensorMap* mb = p.pb[pass] ? &tmB1 : &tmB0;
+        tma_load_2d(sbase + s * kStageBytes, ma, bar_full(s), kb * BK, m0);
+        tma_load_2d(sbase + s * kStageBytes + kABytes, mb, bar_full(s), kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int it = 0; it < total; ++it) {
+        const int s = it % kStages, round = it / kStages;
+        mbar_wait(bar_full(s), round & 1);
+        tc_fence_after();
+        const uint64_t ad = make_desc_sw128(sbase + s * kStageBytes);
+        const uint64_t bd = make_desc_sw128(sbase + s * kStageBytes + kABytes);
+#pragma unroll
+        for (int ks = 0; ks < BK / 16; ++ks)
+          tc_mma(tmem_base, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), kIdesc, (it | ks) != 0);
+        tc_commit(bar_empty(s));  // the stage is free again when these MMAs have read it
+      }
+      tc_commit(bar_acc);
+    }
+  } else {
+    // ---- epilogue: warp w reads TMEM lanes [32 (w % 4), 32 (w % 4) + 32) = rows of the tile
+    const int quad = warp & 3;
+    const int row = m0 + quad * 32 + lane;
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const bool row_ok = row < p.M;
+#pragma unroll 1
+    for (int c32 = 0; c32 < BN / 32; ++c32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + c32 * 32, v);
+      const int n = n0 + c32 * 32;
+      if (!row_ok || n >= p.N) continue;
+      float y[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float t = __uint_as_float(v[j]);
+        if (p.bias) t += __ldg(p.bias + n + j);
+        y[j] = apply_act(t, p.act);
+      }
+      const size_t o = (size_t)row * p.N + n;
+      if (p.out_f32) {
+        float4* q = reinterpret_cast<float4*>(p.out_f32 + o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+      }
+      if (p.out_hi) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+          hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
+          const float2 f = __bfloat1622float2(h2);
+          const __nv_bfloat162 l2 = __floats2bfloat162_rn(y[2 * j] - f.x, y[2 * j + 1] - f.y);
+          lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        uint4* qh = reinterpret_cast<uint4*>(p.out_hi + o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) qh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+        if (p.out_lo) {
+          uint4* ql = reinterpret_cast<uint4*>(p.out_lo + o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ql[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// bf16 [rows][K] row-major, box = 64 (K) x box_rows, 128-byte swizzle
+static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int K, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN>
+static cudaError_t launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
+                          const Params& p, cudaStream_t stream) {
+  constexpr int smem = kStages * (kABytes + BN * BK * 2) + 8 * (2 * kStages + 1) + 16 + 1024;  // + alignment slack
+  cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.N + BN - 1) / BN));
+  gemm_kernel<BN><<<grid, kThreads, smem, stream>>>(a0, a1, b0, b1, p);
+  return cudaGetLastError();
+}
+
+}  // namespace pmgemm
+
+extern "C" int pmnet_gemm_bf16(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                               float* out_f32, void* out_hi, void* out_lo, int64_t M, int32_t N, int32_t K, int32_t act,
+                               void* stream_) {
+  using namespace pmgemm;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!a_hi || !w_hi || (!out_f32 && !out_hi) || (out_lo && !out_hi) || ((a_lo == nullptr) != (w_lo == nullptr))) {
+    pmnet_set_error("pmnet_gemm_bf16: null / inconsistent argument");
+    return PMNET_EINVAL;
+  }
+  if (M <= 0 || N <= 0 || K <= 0 || (K & 7) || (N % 32) || M > 0x7fffffffLL) {
+    pmnet_set_error("pmnet_gemm_bf16: K must be a multiple of 8 and N a multiple of 32");
+    return PMNET_EINVAL;
+  }
+  const int BN = (N % 192 == 0) ? 192 : 96;
+  if (N % 96 != 0 && N > 96) {
+    pmnet_set_error("pmnet_gemm_bf16: N must be <= 96 or a multiple of 96");
+    return PMNET_EINVAL;
+  }
+  CUtensorMap a0, a1, b0, b1;
+  bool ok = make_map(&a0, a_hi, M, K, BM) && make_map(&b0, w_hi, N, K, BN);
+  if (ok && a_lo) ok = make_map(&a1, a_lo, M, K, BM) && make_map(&b1, w_lo, N, K, BN);
+  if (!ok) {
+    pmnet_set_error("pmnet_gemm_bf16: cuTensorMapEncodeTiled failed (operands must be 16-byte aligned)");
+    return PMNET_ECUDA;
+  }
+  if (!a_lo) {
+    a1 = a0;
+    b1 = b0;
+  }
+  Params p;
+  p.M = (int)M; p.N = N; p.K = K;
+  p.npass = a_lo ? 3 : 1;
+  p.pa[0] = 0; p.pb[0] = 0;
+  p.pa[1] = 1; p.pb[1] = 0;
+  p.pa[2] = 0; p.pb[2] = 1;
+  p.bias = bias;
+  p.out_f32 = out_f32;
+  p.out_hi = (__nv_bfloat16*)out_hi;
+  p.out_lo = (__nv_bfloat16*)out_lo;
+  p.act = act;
+  const cudaError_t e = BN == 192 ? launch<192>(a0, a1, b0, b1, p, stream) : launch<96>(a0, a1, b0, b1, p, stream);
+  if (e != cudaSuccess) {
+    pmnet_set_error(cudaGetErrorString(e));
+    return PMNET_ECUDA;
+  }
+  return PMNET_OK;
+}

@@ -25,14 +25,23 @@
 
 namespace fastk {
 
-constexpr int TC = 88;      // (level, model cluster) entries per ligand (88: keeps the CTA under the 164 KB carve-out)
+#ifndef PM_FAST_TC
+#define PM_FAST_TC 88
+#endif
+#ifndef PM_FAST_WARPS
+#define PM_FAST_WARPS 32
+#endif
+#ifndef PM_FAST_PREFETCH
+#define PM_FAST_PREFETCH 1
+#endif
+constexpr int TC = PM_FAST_TC;  // (level, model cluster) entries per ligand (88: keeps the CTA under the 164 KB carve-out)
 constexpr int RC = 224;     // node-match records per ligand
 constexpr int LC = 12;      // levels
 constexpr int NLC = 48;     // ligand nodes in the selected levels
 constexpr int MKW = 384;    // words of the triangular mask stack
 constexpr int ROWS = 2048;  // pair-score rows per warp
 constexpr int PC = 4096;    // pair entries per warp
-constexpr int kWarps = 32;  // one 1024-thread CTA per SM at 64 registers per thread
+constexpr int kWarps = PM_FAST_WARPS;  // one 1024-thread CTA per SM at 64 registers per thread
 constexpr int kNoBase = INT32_MIN;  // lane a of my_pbase: the node at depth a is a None node (pair bases may be negative)
 
 // per-warp global scratch, byte offsets from the warp's base (every per-conformer row is 128 B, lane = conformer)
@@ -586,6 +595,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) pmnet_score_fast_kernel(const 
               const int found = ws.lev_start[y] + src;
               const unsigned alive2 = pm[found];
               ++st_nodes;
+#if PM_FAST_PREFETCH
               const int myrow = (pf_found == found) ? pf_row : (is_anc ? prow[my_pbase + found] : -1);
               // the next sibling's row indices are requested now (used unless this child is pushed in between)
               pf_found = -1;
@@ -593,6 +603,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) pmnet_score_fast_kernel(const 
                 pf_found = ws.lev_start[y] + __ffs(cand) - 1;
                 pf_row = is_anc ? prow[my_pbase + pf_found] : -1;
               }
+#else
+              const int myrow = is_anc ? prow[my_pbase + found] : -1;
+#endif
               const unsigned sr = ws.srow[found];
               const int pbc = ws.rowbase[found];
               // the child's candidate masks: parent mask & conformers alive in the child & pair validity

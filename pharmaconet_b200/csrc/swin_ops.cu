@@ -54,6 +54,25 @@ __device__ __forceinline__ void store_row32(float* p, const float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
+// two-term bf16 split of 32 values: hi = bf16(v), lo = bf16(v - hi) (the operand pair of a split-precision GEMM)
+__device__ __forceinline__ void store_row32_split(__nv_bfloat16* hi, __nv_bfloat16* lo, const float (&v)[32]) {
+  uint32_t h[16], l[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    h[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    const float2 f = __bfloat1622float2(h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+    l[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  uint4* qh = reinterpret_cast<uint4*>(hi);
+  uint4* ql = reinterpret_cast<uint4*>(lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    qh[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+    ql[i] = make_uint4(l[4 * i], l[4 * i + 1], l[4 * i + 2], l[4 * i + 3]);
+  }
+}
 
 constexpr int kHeadDim = 32;
 constexpr int kTokens = 64;  // 4^3 window
@@ -64,7 +83,8 @@ __global__ void __launch_bounds__(kTokens) window_attention_kernel(const T* __re
                                                                    const float* __restrict__ scale,
                                                                    const float* __restrict__ rel_bias,
                                                                    const float* __restrict__ mask, int res, int shift,
-                                                                   int heads) {
+                                                                   int heads, __nv_bfloat16* __restrict__ out_hi,
+                                                                   __nv_bfloat16* __restrict__ out_lo) {
   __shared__ __align__(16) float ks[kTokens][kHeadDim];  // every thread reads the same row: broadcast, no conflicts
   __shared__ __align__(16) float vs[kTokens][kHeadDim];
   const int t = threadIdx.x, h = blockIdx.y;
@@ -144,7 +164,8 @@ __global__ void __launch_bounds__(kTokens) window_attention_kernel(const T* __re
       o[4 * i + 3] = fmaf(p, v4.w, o[4 * i + 3]);
     }
   }
-  store_row32(out + tok * C + h * kHeadDim, o);
+  if (out) store_row32(out + tok * C + h * kHeadDim, o);
+  if (out_hi) store_row32_split(out_hi + tok * C + h * kHeadDim, out_lo + tok * C + h * kHeadDim, o);
 }
 
 
@@ -300,7 +321,9 @@ __global__ void __launch_bounds__(32) window_attention_mma_kernel(const __nv_bfl
 template <typename T, int PER>
 __global__ void __launch_bounds__(256) ln_residual_kernel(const float* __restrict__ shortcut, const T* __restrict__ hsrc,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          float* __restrict__ y, int64_t rows, float eps) {
+                                                          float* __restrict__ y, int64_t rows, float eps,
+                                                          __nv_bfloat16* __restrict__ y_hi,
+                                                          __nv_bfloat16* __restrict__ y_lo) {
   constexpr int C = 32 * PER;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -331,18 +354,23 @@ __global__ void __launch_bounds__(256) ln_residual_kernel(const float* __restric
     float r = (v[i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
     if (sp) r += sp[c];
     yp[c] = r;
+    if (y_hi) {  // the GEMM operand(s) of the next linear layer
+      const __nv_bfloat16 hb = __float2bfloat16_rn(r);
+      y_hi[row * C + c] = hb;
+      if (y_lo) y_lo[row * C + c] = __float2bfloat16_rn(r - __bfloat162float(hb));
+    }
   }
 }
 
 template <typename T>
 cudaError_t launch_ln(const float* shortcut, const T* h, const float* gamma, const float* beta, float* y, int64_t rows,
-                      int C, float eps, cudaStream_t stream) {
+                      int C, float eps, cudaStream_t stream, __nv_bfloat16* y_hi = nullptr, __nv_bfloat16* y_lo = nullptr) {
   const unsigned blocks = (unsigned)((rows + 7) / 8);
   switch (C / 32) {
-    case 3: ln_residual_kernel<T, 3><<<blocks, 256, 0, stream>>>(shortcut, h, gamma, beta, y, rows, eps); break;
-    case 6: ln_residual_kernel<T, 6><<<blocks, 256, 0, stream>>>(shortcut, h, gamma, beta, y, rows, eps); break;
-    case 12: ln_residual_kernel<T, 12><<<blocks, 256, 0, stream>>>(shortcut, h, gamma, beta, y, rows, eps); break;
-    case 24: ln_residual_kernel<T, 24><<<blocks, 256, 0, stream>>>(shortcut, h, gamma, beta, y, rows, eps); break;
+    case 3: ln_residual_kernel<T, 3><<<blocks, 256, 0, stream>>>(shortcut, h, gamma, beta, y, rows, eps, y_hi, y_lo); break;
+    case 6: ln_residual_kernel<T, 6><<<blocks, 256, 0, stream>>>(shortcut, h, gamma, beta, y, rows, eps, y_hi, y_lo); break;
+    case 12: ln_residual_kernel<T, 12><<<blocks, 256, 0, stream>>>(shortcut, h, gamma, beta, y, rows, eps, y_hi, y_lo); break;
+    case 24: ln_residual_kernel<T, 24><<<blocks, 256, 0, stream>>>(shortcut, h, gamma, beta, y, rows, eps, y_hi, y_lo); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -371,7 +399,32 @@ int pmnet_window_attention(const void* qkv, void* out, const float* logit_scale,
                                                          rel_bias, attn_mask, res, shift, heads);
   else
     window_attention_kernel<float><<<grid, kTokens, 0, stream>>>((const float*)qkv, (float*)out, logit_scale, rel_bias,
-                                                                 attn_mask, res, shift, heads);
+                                                                 attn_mask, res, shift, heads, nullptr, nullptr);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    pmnet_set_error(cudaGetErrorString(e));
+    return PMNET_ECUDA;
+  }
+  return PMNET_OK;
+}
+
+// fp32 qkv in, result as the two-term bf16 split the projection GEMM consumes (split-precision backbone)
+int pmnet_window_attention_split(const float* qkv, void* out_hi, void* out_lo, const float* logit_scale,
+                                 const float* rel_bias, const float* attn_mask, int32_t B, int32_t res, int32_t shift,
+                                 int32_t heads, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!qkv || !out_hi || !out_lo || !logit_scale || !rel_bias) {
+    pmnet_set_error("pmnet_window_attention_split: null argument");
+    return PMNET_EINVAL;
+  }
+  if (B <= 0 || res < 4 || (res & 3) || heads <= 0 || shift < 0 || shift >= 4) {
+    pmnet_set_error("pmnet_window_attention_split: resolution must be a multiple of the 4^3 window");
+    return PMNET_EINVAL;
+  }
+  const int nw = (res / 4) * (res / 4) * (res / 4);
+  dim3 grid((unsigned)(B * nw), (unsigned)heads);
+  window_attention_kernel<float><<<grid, kTokens, 0, stream>>>(qkv, nullptr, logit_scale, rel_bias, attn_mask, res, shift,
+                                                               heads, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     pmnet_set_error(cudaGetErrorString(e));
@@ -382,8 +435,14 @@ int pmnet_window_attention(const void* qkv, void* out, const float* logit_scale,
 
 int pmnet_ln_residual(const float* shortcut, const void* h, int32_t h_is_bf16, const float* gamma, const float* beta,
                       float* y, int64_t rows, int32_t C, float eps, void* stream_) {
+  return pmnet_ln_residual_split(shortcut, h, h_is_bf16, gamma, beta, y, nullptr, nullptr, rows, C, eps, stream_);
+}
+
+int pmnet_ln_residual_split(const float* shortcut, const void* h, int32_t h_is_bf16, const float* gamma,
+                            const float* beta, float* y, void* y_hi, void* y_lo, int64_t rows, int32_t C, float eps,
+                            void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!h || !gamma || !beta || !y) {
+  if (!h || !gamma || !beta || !y || (y_lo && !y_hi)) {
     pmnet_set_error("pmnet_ln_residual: null argument");
     return PMNET_EINVAL;
   }
@@ -391,8 +450,10 @@ int pmnet_ln_residual(const float* shortcut, const void* h, int32_t h_is_bf16, c
     pmnet_set_error("pmnet_ln_residual: C must be 96, 192, 384 or 768 (the Swin stage widths)");
     return PMNET_EINVAL;
   }
-  cudaError_t e = h_is_bf16 ? launch_ln<__nv_bfloat16>(shortcut, (const __nv_bfloat16*)h, gamma, beta, y, rows, C, eps, stream)
-                            : launch_ln<float>(shortcut, (const float*)h, gamma, beta, y, rows, C, eps, stream);
+  cudaError_t e = h_is_bf16 ? launch_ln<__nv_bfloat16>(shortcut, (const __nv_bfloat16*)h, gamma, beta, y, rows, C, eps, stream,
+                                                       (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo)
+                            : launch_ln<float>(shortcut, (const float*)h, gamma, beta, y, rows, C, eps, stream,
+                                               (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
   if (e != cudaSuccess) {
     pmnet_set_error(cudaGetErrorString(e));
     return PMNET_ECUDA;

@@ -22,6 +22,7 @@ ap.add_argument("--warps", type=int, default=0)
 ap.add_argument("--blocks", type=int, default=0)
 ap.add_argument("--rows", type=int, default=0)
 ap.add_argument("--tiny", action="store_true")
+ap.add_argument("--lpt", action="store_true", help="hand out ligands longest first (scoring.cost_order), like the bench")
 ap.add_argument("--hotspots", type=int, default=0, help="build a synthetic model with this many hotspots instead of syn0")
 a = ap.parse_args()
 
@@ -37,6 +38,8 @@ print(f"generated {a.unique} ligands in {time.time()-t:.1f}s", flush=True)
 idx = np.tile(np.arange(a.unique), a.rep)
 big = base.select(idx) if a.rep > 1 else base
 db = scoring.DeviceLigandBatch.from_host(big, "cuda:0")
+if a.lpt:
+    db.set_order(scoring.cost_order(dm, db))
 cfg = scoring.ScoreConfig(a.warps, a.blocks, a.rows)
 n = big.num_ligands
 print(f"library: {n} ligands, {big.num_conformers_total} conformers, {db.nbytes()/1e6:.1f} MB", flush=True)
