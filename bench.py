@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--ref-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg (real reference)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cnn", action="store_true", help="skip the CNN forward leg (BASELINE configs[3])")
     return ap.parse_args()
 
 
@@ -190,6 +191,91 @@ def conv_leg(dev, batch: int = 8, iters: int = 10):
         "workload": f"{batch} x 96ch x 64^3 -> 96ch, 3x3x3, fused BN+ReLU, bf16 operands / fp32 accumulate",
         "peak_source": src,
     }  # fmt: skip
+
+
+def cnn_forward_leg(dev, batch: int = 64, chunk: int = 8, iters: int = 2):
+    """BASELINE configs[3]: the CNN forward (forward_feature + cavity extraction + token prediction) over `batch`
+    synthetic 64^3 pockets in chunks of `chunk`, seeded synthetic weights (no trained checkpoint exists offline), in
+    both precisions of this package, next to the unmodified reference nn.Modules (oracle/_ref) through torch / cuDNN on
+    the same GPU. Algorithmic FLOPs per pocket: 479.9 G."""
+    import numpy as np
+    import torch
+
+    from pharmaconet_b200 import cnn, cnn_weights
+
+    G = os.path.join(ROOT, "tests", "golden")
+    with open(os.path.join(G, "cnn_manifest.json")) as f:
+        man = json.load(f)
+    buf = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, "cnn_buffers.npz")).items()}
+    sd = cnn_weights.synth_state_dict(man, buf, 0)
+    model = cnn.PharmacoNetModel(sd, dev)
+    g = torch.Generator().manual_seed(0)
+    images = torch.rand((chunk, 33, 64, 64, 64), generator=g).to(dev)
+    tokens = torch.cat([torch.randint(0, 64, (200, 3), generator=g), torch.randint(0, 10, (200, 1), generator=g)], 1).long().to(dev)
+    n_chunks = max(1, batch // chunk)
+    flop = 479.9e9
+    peak, src = 1450.0, "fallback (B200_PROFILING.md)"
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            peak, src = float(json.load(f)["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+
+    def timed(fn):
+        fn()  # warm-up (also builds the cached weight operands)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            for _ in range(n_chunks):
+                fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / (iters * n_chunks * chunk)  # ms per pocket
+
+    def ours():
+        feats = model.forward_feature(images, nchw=False)
+        model.forward_cavity_extraction(feats[-1])
+        model.forward_token_prediction(feats[-1], [tokens] * chunk)
+
+    out = {
+        "workload": f"{batch} synthetic 64^3 x 33-channel pockets in chunks of {chunk}, 200 tokens each: forward_feature + "
+                    "cavity extraction + token prediction (BASELINE configs[3]); seeded synthetic weights",
+        "flop_per_pocket": flop, "peak": peak, "peak_unit": "TFLOP/s", "peak_source": src,
+    }  # fmt: skip
+    for prec in ("bf16x3", "bf16"):
+        model.precision = prec
+        ms = timed(ours)
+        out[prec] = {"ms_per_pocket": ms, "tflops_algorithmic": flop / ms / 1e9, "frac_of_peak": flop / ms / 1e9 / peak}
+    out["bf16x3"]["note"] = "two-term bf16 operands, 3 tensor-core passes per product: integer outputs follow the fp32 reference"
+    out["bf16"]["note"] = "single pass on bf16 operands"
+    del model
+    # the reference's own modules on this GPU (torch / cuDNN; TF32 convolutions are torch's default)
+    try:
+        import ref_harness
+
+        ref_harness.import_reference()
+        from pmnet.network import build_model
+
+        ref = build_model({}).eval()
+        ref.load_state_dict(sd, strict=True)
+        ref = ref.to(dev)
+
+        def theirs():
+            with torch.no_grad():
+                feats = ref.forward_feature(images)
+                ref.forward_cavity_extraction(feats[-1])
+                ref.forward_token_prediction(feats[-1], [tokens] * chunk)
+
+        ms = timed(theirs)
+        out["reference_modules_same_gpu"] = {
+            "ms_per_pocket": ms, "tflops_algorithmic": flop / ms / 1e9,
+            "note": "unmodified pmnet.network modules (oracle/_ref) through torch/cuDNN, fp32 weights, TF32 convolutions",
+        }  # fmt: skip
+        del ref
+    except Exception as e:  # noqa: BLE001
+        out["reference_modules_same_gpu"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+    return out
 
 
 def host_prefix(dev_lib, n):
@@ -533,6 +619,13 @@ def main():
         except Exception as e:  # noqa: BLE001 - the headline metric must still be printed
             conv_roofline = {"error": repr(e)}
 
+    cnn_forward = None
+    if rank == 0 and world == 1 and not args.no_cnn:
+        try:
+            cnn_forward = cnn_forward_leg(dev)
+        except Exception as e:  # noqa: BLE001
+            cnn_forward = {"error": repr(e)}
+
     if rank == 0:
         peak, peak_src = load_peaks()
         achieved = alg_bytes / (kernel_ms_avg * 1e-3) / 1e9
@@ -566,6 +659,7 @@ def main():
             },
             "issue_roofline": issue,
             "cnn_conv3d_roofline": conv_roofline,
+            "cnn_forward": cnn_forward,
             "cpu_baseline": cpu_baseline, "cpu_port": cpu_port, "parity": parity, "clocks": clocks,
             "top1": {"id": int(top_ids[0]), "score": float(res.topk_scores[0].item())},
         }  # fmt: skip

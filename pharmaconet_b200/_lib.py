@@ -72,7 +72,9 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if is_stale() and _nvcc() is not None:  # missing, or older than a source / header (an edited .cu must not run stale)
+    # missing, or older than a source / header (an edited .cu must not run stale). A developer override
+    # (PMNET_B200_SO = an A/B variant built with other flags) is loaded as it is.
+    if not os.environ.get("PMNET_B200_SO") and is_stale() and _nvcc() is not None:
         build()
     L = C.CDLL(SO_PATH)
     L.pmnet_abi_version.restype = C.c_int

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import _lib, conv
+from . import _lib, conv, gemm
 from .swin import SwinV2Backbone
 
 _FEATURE_CHANNELS = (33, 96, 192, 384, 768)  # builder.py:27
@@ -82,15 +82,52 @@ class PharmacoNetModel:
         self.mask_logit_w = sd["mask_head.conv_logits.weight"].reshape(96).float().contiguous()
         self.mask_logit_b = float(sd["mask_head.conv_logits.bias"].item())
         self._L = _lib.lib()
+        self._wops: dict = {}
         # "bf16": every convolution is one tcgen05 pass on bf16 operands (fastest; ~2^-8 relative error per layer, a
         # few hundred of 262144 mask voxels differ from the fp32 reference). "bf16x3": activations and weights of the
         # convolution stack travel as two-term bf16 splits and every convolution is three passes (~2^-16 relative
         # error per product): the precision mode for outputs that feed a threshold (module.py:232-233, 288).
+        self._precision = "bf16"
         self.precision = "bf16"
 
     @property
     def split(self) -> bool:
         return self.precision == "bf16x3"
+
+    @property
+    def precision(self) -> str:
+        return self._precision
+
+    @precision.setter
+    def precision(self, value: str) -> None:
+        if value not in ("bf16", "bf16x3"):
+            raise ValueError("precision must be 'bf16' or 'bf16x3'")
+        self._precision = value
+        self.backbone.precision = value  # the backbone's linear layers follow (csrc/gemm.cu)
+
+    def _linear(self, x: torch.Tensor, key, weight: torch.Tensor, bias: torch.Tensor | None = None, act: int = 0):
+        """fp32 [M, K] x weight[N, K]^T (+ bias, activation) on the tcgen05 GEMM in the model's precision -> fp32 [M, N].
+        The weight operand is split / converted once and cached under `key`."""
+        ck = (key, self.split)
+        w = self._wops.get(ck)
+        if w is None:
+            w = self._wops[ck] = gemm.Operand.from_float(weight, self.split)
+        n = weight.shape[0]
+        if n % 32:  # e.g. the 1-wide score layer: pad the outputs to the GEMM's granularity and slice
+            npad = (n + 31) // 32 * 32
+            ck = (key, self.split, "pad")
+            wp = self._wops.get(ck)
+            if wp is None:
+                wpad = torch.zeros((npad, weight.shape[1]), dtype=torch.float32, device=weight.device)
+                wpad[:n] = weight
+                bpad = torch.zeros(npad, dtype=torch.float32, device=weight.device)
+                if bias is not None:
+                    bpad[:n] = bias
+                wp = self._wops[ck] = (gemm.Operand.from_float(wpad, self.split), bpad)
+            y, _ = gemm.linear(gemm.Operand.from_float(x, self.split), wp[0], wp[1], act)
+            return y[:, :n]
+        y, _ = gemm.linear(gemm.Operand.from_float(x, self.split), w, bias.float().contiguous() if bias is not None else None, act)
+        return y
 
     # ------------------------------------------------------------------ kernels
     def _k3(self, x: "conv.Act", layer: _ConvBN, head=None, store_out=True):
@@ -110,9 +147,10 @@ class PharmacoNetModel:
             B, _, D, H, W = x.shape
             x = x.contiguous().float()
             if D * H * W <= 4096 and affine:
-                # 8^3 / 16^3 levels with 384 / 192 input channels: < 0.2 GFLOP, but a 75-150 KB weight tile per CTA
-                # - a plain library GEMM plus a few tiny elementwise ops is faster than the fused kernel here
-                y = torch.einsum("bcv,oc->bov", x.reshape(B, layer.cin, -1), layer.w_t.t()).reshape(B, 96, D, H, W)
+                # 8^3 / 16^3 levels with 384 / 192 input channels: < 0.2 GFLOP, but a 75-150 KB weight tile per CTA for
+                # the fused CUDA-core kernel - here the 1x1 conv is the tcgen05 GEMM over the voxels
+                xt = x.reshape(B, layer.cin, -1).transpose(1, 2).reshape(-1, layer.cin)  # [B * V, C_in]
+                y = self._linear(xt, ("lat", id(layer)), layer.w_t.t()).view(B, D, H, W, 96).permute(0, 4, 1, 2, 3)
                 y = torch.relu(y * layer.scale.view(1, -1, 1, 1, 1) + layer.bias.view(1, -1, 1, 1, 1))
                 if up is not None:
                     y = y + F.interpolate(up.float_ncdhw(), scale_factor=2, mode="nearest")
@@ -159,9 +197,7 @@ class PharmacoNetModel:
         B4, C4, D4 = x4.shape[0], x4.shape[1], x4.shape[2]
         cols = F.pad(x4, (1, 1, 1, 1, 1, 1)).unfold(2, 3, 1).unfold(3, 3, 1).unfold(4, 3, 1)  # [B, C, D, H, W, 3, 3, 3]
         cols = cols.permute(0, 2, 3, 4, 1, 5, 6, 7).reshape(B4 * D4**3, C4 * 27)
-        if not hasattr(top, "w2d"):
-            top.w2d = top.weight.reshape(96, -1).float().contiguous()
-        y = (cols @ top.w2d.t()).view(B4, D4, D4, D4, 96).permute(0, 4, 1, 2, 3)
+        y = self._linear(cols, "fpn_top", top.weight.reshape(96, -1)).view(B4, D4, D4, D4, 96).permute(0, 4, 1, 2, 3)
         y = torch.relu(y * top.scale.view(1, -1, 1, 1, 1) + top.bias.view(1, -1, 1, 1, 1))
         fpn = self._k3(conv.to_act(y, self.split), self.fpn_convs[4][1])[0]
         outs = [fpn]
@@ -225,15 +261,18 @@ class PharmacoNetModel:
         if x.lo is not None:
             voxel = voxel + x.lo[bidx, :, allt[:, 0], allt[:, 1], allt[:, 2], :].reshape(-1, 96).float()
         h0 = torch.cat([voxel, sd["token_head.interaction_embedding.weight"][allt[:, 3]]], dim=1)
-        skip = F.linear(h0, sd["token_head.skip.weight"], sd["token_head.skip.bias"]) if "token_head.skip.weight" in sd else h0
+        def lin(x, name, act=0):
+            return self._linear(x, name, sd[name + ".weight"], sd[name + ".bias"], act)
+
+        skip = lin(h0, "token_head.skip") if "token_head.skip.weight" in sd else h0
         h = h0
         for i in (0, 2, 4):
-            h = F.silu(F.linear(h, sd[f"token_head.feature_mlp.{i}.weight"], sd[f"token_head.feature_mlp.{i}.bias"]))
+            h = lin(h, f"token_head.feature_mlp.{i}", gemm.ACT_SILU)
         tf = skip + h
         s = tf
         for i in (0, 2):
-            s = torch.relu(F.linear(s, sd[f"token_head.score_mlp.{i}.weight"], sd[f"token_head.score_mlp.{i}.bias"]))
-        s = F.linear(s, sd["token_head.score_mlp.4.weight"], sd["token_head.score_mlp.4.bias"]).squeeze(-1)
+            s = lin(s, f"token_head.score_mlp.{i}", gemm.ACT_RELU)
+        s = lin(s, "token_head.score_mlp.4").squeeze(-1)
         return list(torch.split(s, counts)), list(torch.split(tf, counts))
 
     # ------------------------------------------------------------------ detector.py:73-91, mask_head.py:38-196
@@ -302,12 +341,14 @@ class PharmacoNetModel:
                 for level in (4, 3, 2, 1, 0):
                     s = shared[level]
                     pvox = pvox_levels[level, lo:hi].contiguous()
-                    bg = F.linear(tfeat[lo:hi], sd[f"mask_head.background_mlp_list.{level}.weight"], sd[f"mask_head.background_mlp_list.{level}.bias"])
-                    pt = F.linear(tfeat[lo:hi], sd[f"mask_head.point_mlp_list.{level}.weight"], sd[f"mask_head.point_mlp_list.{level}.bias"])
+                    bgn, ptn = f"mask_head.background_mlp_list.{level}", f"mask_head.point_mlp_list.{level}"
+                    bg = self._linear(tfeat[lo:hi], bgn, sd[bgn + ".weight"], sd[bgn + ".bias"])
+                    pt = self._linear(tfeat[lo:hi], ptn, sd[ptn + ".weight"], sd[ptn + ".bias"])
                     lat = self.mask_lateral[level]
                     if lat is not None:  # push the per-box vectors through the (linear) 1x1 conv
                         wl = lat.weight.reshape(96, 96).float()
-                        bg, pt = bg @ wl.t(), pt @ wl.t()
+                        bg = self._linear(bg, ("mask_lat", level), wl)
+                        pt = self._linear(pt, ("mask_lat", level), wl)
                     fpn = self._combine(s, bg.contiguous(), pt.contiguous(), pvox, lat, fpn)
                     convs = self.mask_convs[level]
                     for i, layer in enumerate(convs):

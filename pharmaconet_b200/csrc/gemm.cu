@@ -8,8 +8,8 @@
 // Operands are bf16, K-major (row-major with K contiguous), fetched by TMA as 64-element (128 B) wide boxes with the
 // 128-byte swizzle; accumulation is fp32 in TMEM. One CTA computes one 128 x BN output tile (BN = 96 or 192: every
 // layer width of the network is a multiple of 96) through a 4-stage TMA -> tcgen05.mma pipeline:
-//   warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-5 = epilogue (TMEM -> registers -> bias / GELU ->
-//   fp32 and / or bf16 stores; TMEM lane quadrant = warp % 4).
+//   warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2.. = epilogue (12 or 24 of them) (TMEM -> registers -> bias / GELU ->
+//   fp32 and / or bf16 stores; TMEM lane quadrant = warp % 4, column group = (warp - 2) / 4).
 // Split precision: with a_lo / w_lo given the K loop runs three times over (a_hi, w_hi), (a_lo, w_hi), (a_hi, w_lo) into
 // the SAME accumulator - x w = x_hi w_hi + x_lo w_hi + x_hi w_lo to 2^-16 relative - and the epilogue can emit the
 // (hi, lo) pair of its result for the next layer. Out-of-range rows / columns / K tails are zero-filled by TMA.
@@ -25,8 +25,10 @@ extern void pmnet_set_error(const char* msg);
 
 namespace pmgemm {
 
-constexpr int BM = 128, BK = 64, kStages = 4;
-constexpr int kThreads = 192;
+constexpr int BM = 128, BK = 64;
+// epilogue warps: one per (TMEM lane quadrant, 32-column chunk of the tile) = 12 for BN = 96, 24 for BN = 192
+__host__ __device__ constexpr int epi_warps(int bn) { return 4 * (bn / 32); }
+__host__ __device__ constexpr int threads(int bn) { return 64 + 32 * epi_warps(bn); }  // + TMA producer warp + MMA issuer warp
 constexpr int kABytes = BM * BK * 2;  // 16384
 
 struct Params {
@@ -46,6 +48,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -112,36 +117,46 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
-                                                           const __grid_constant__ CUtensorMap tmA1,
-                                                           const __grid_constant__ CUtensorMap tmB0,
-                                                           const __grid_constant__ CUtensorMap tmB1, const Params p) {
+// Persistent: the grid is one CTA per SM (two for the short-K shape, whose two pipeline stages leave room) and every CTA
+// walks output tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n tile fastest, so that the CTAs working at the same
+// time share their A rows in L2). Barrier init, TMEM allocation and the tensor-map fetch are paid once per CTA, and the
+// accumulator is double buffered in TMEM: the epilogue of tile i overlaps the loads and MMAs of tile i + 1.
+// kStages = 4 for long K loops; 2 for the short ones (K = 96 ... 256 with up to three passes).
+template <int BN, int kStages>
+__global__ void __launch_bounds__(threads(BN)) gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                        const __grid_constant__ CUtensorMap tmA1,
+                                                        const __grid_constant__ CUtensorMap tmB0,
+                                                        const __grid_constant__ CUtensorMap tmB1, const Params p) {
   constexpr int kBBytes = BN * BK * 2;
   constexpr int kStageBytes = kABytes + kBBytes;
-  constexpr uint32_t kTmemCols = BN <= 128 ? 128 : 256;
+  constexpr uint32_t kTmemCols = 2 * BN <= 256 ? 256 : 512;  // two accumulators of BN columns
   // instruction descriptor, kind::f16: D = f32 (bit 4), A = B = bf16 (bits 7, 10), K-major, N >> 3 at 17, M >> 4 at 24
   constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // the swizzled tiles need 1024-byte alignment in the shared window: align explicitly (1 KB of slack is allocated)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bars = sbase + kStages * kStageBytes;  // full[4], empty[4], accfull
+  const uint32_t bars = sbase + kStages * kStageBytes;  // full[kStages], empty[kStages], accfull[2], accempty[2]
   auto bar_full = [&](int s) { return bars + 8u * s; };
   auto bar_empty = [&](int s) { return bars + 8u * (kStages + s); };
-  const uint32_t bar_acc = bars + 8u * (2 * kStages);
-  volatile uint32_t* tmem_ptr_smem = (volatile uint32_t*)(smem + kStages * kStageBytes + 8 * (2 * kStages + 1));
+  auto bar_accfull = [&](int b) { return bars + 8u * (2 * kStages + b); };
+  auto bar_accempty = [&](int b) { return bars + 8u * (2 * kStages + 2 + b); };
+  volatile uint32_t* tmem_ptr_smem = (volatile uint32_t*)(smem + kStages * kStageBytes + 8 * (2 * kStages + 4));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int kblocks = (p.K + BK - 1) / BK;
-  const int total = kblocks * p.npass;
+  const int per_tile = kblocks * p.npass;
+  const int n_tiles_n = (p.N + BN - 1) / BN;
+  const int n_tiles = ((p.M + BM - 1) / BM) * n_tiles_n;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), 1);
     }
-    mbar_init(bar_acc, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_accfull(b), 1);
+      mbar_init(bar_accempty(b), epi_warps(BN));  // one arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -158,77 +173,99 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < total; ++it) {
-        const int pass = it / kblocks, kb = it - pass * kblocks;
-        const int s = it % kStages, round = it / kStages;
-        mbar_wait(bar_empty(s), (round & 1) ^ 1);
-        mbar_expect_tx(bar_full(s), kStageBytes);
-        const CUtensorMap* ma = p.pa[pass] ? &tmA1 : &tmA0;
-        const CUtensorMap* mb = p.pb[pass] ? &tmB1 : &tmB0;
-        tma_load_2d(sbase + s * kStageBytes, ma, bar_full(s), kb * BK, m0);
-        tma_load_2d(sbase + s * kStageBytes + kABytes, mb, bar_full(s), kb * BK, n0);
+      uint32_t it = 0;  // k iterations issued so far, across tiles
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+        for (int j = 0; j < per_tile; ++j, ++it) {
+          const int pass = j / kblocks, kb = j - pass * kblocks;
+          const uint32_t s = it % kStages, round = it / kStages;
+          mbar_wait(bar_empty(s), (round & 1) ^ 1);
+          mbar_expect_tx(bar_full(s), kStageBytes);
+          const CUtensorMap* ma = p.pa[pass] ? &tmA1 : &tmA0;
+          const CUtensorMap* mb = p.pb[pass] ? &tmB1 : &tmB0;
+          tma_load_2d(sbase + s * kStageBytes, ma, bar_full(s), kb * BK, m0);
+          tma_load_2d(sbase + s * kStageBytes + kABytes, mb, bar_full(s), kb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int it = 0; it < total; ++it) {
-        const int s = it % kStages, round = it / kStages;
-        mbar_wait(bar_full(s), round & 1);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t buf = tcount & 1;
+        mbar_wait(bar_accempty(buf), ((tcount >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint64_t ad = make_desc_sw128(sbase + s * kStageBytes);
-        const uint64_t bd = make_desc_sw128(sbase + s * kStageBytes + kABytes);
+        const uint32_t tacc = tmem_base + buf * BN;
+        for (int j = 0; j < per_tile; ++j, ++it) {
+          const uint32_t s = it % kStages, round = it / kStages;
+          mbar_wait(bar_full(s), round & 1);
+          tc_fence_after();
+          const uint64_t ad = make_desc_sw128(sbase + s * kStageBytes);
+          const uint64_t bd = make_desc_sw128(sbase + s * kStageBytes + kABytes);
 #pragma unroll
-        for (int ks = 0; ks < BK / 16; ++ks)
-          tc_mma(tmem_base, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), kIdesc, (it | ks) != 0);
-        tc_commit(bar_empty(s));  // the stage is free again when these MMAs have read it
+          for (int ks = 0; ks < BK / 16; ++ks)
+            tc_mma(tacc, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), kIdesc, (j | ks) != 0);
+          tc_commit(bar_empty(s));  // the stage is free again when these MMAs have read it
+        }
+        tc_commit(bar_accfull(buf));
       }
-      tc_commit(bar_acc);
     }
   } else {
-    // ---- epilogue: warp w reads TMEM lanes [32 (w % 4), 32 (w % 4) + 32) = rows of the tile
+    // ---- epilogue: warp w reads TMEM lanes [32 (w % 4), 32 (w % 4) + 32) = rows of the tile and ONE 32-column chunk:
+    // a single warp per quadrant could not keep up with the tensor pipe (bias + GELU + bf16 split of 128 x 192 values is
+    // ~10^4 dependent instructions per thread; measured 968 -> 437 us for the stage-0 fc1 with 4 -> 12 warps)
     const int quad = warp & 3;
-    const int row = m0 + quad * 32 + lane;
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    const bool row_ok = row < p.M;
+    const int cgroup = (warp - 2) >> 2;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+      const uint32_t buf = tcount & 1;
+      const int row = m0 + quad * 32 + lane;
+      mbar_wait(bar_accfull(buf), (tcount >> 1) & 1);
+      tc_fence_after();
+      const bool row_ok = row < p.M;
 #pragma unroll 1
-    for (int c32 = 0; c32 < BN / 32; ++c32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + c32 * 32, v);
-      const int n = n0 + c32 * 32;
-      if (!row_ok || n >= p.N) continue;
-      float y[32];
+      for (int c32 = cgroup; c32 < BN / 32; c32 += epi_warps(BN) / 4) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN + c32 * 32, v);
+        const int n = n0 + c32 * 32;
+        if (!row_ok || n >= p.N) continue;
+        float y[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float t = __uint_as_float(v[j]);
-        if (p.bias) t += __ldg(p.bias + n + j);
-        y[j] = apply_act(t, p.act);
-      }
-      const size_t o = (size_t)row * p.N + n;
-      if (p.out_f32) {
-        float4* q = reinterpret_cast<float4*>(p.out_f32 + o);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) q[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-      }
-      if (p.out_hi) {
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
-          hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
-          const float2 f = __bfloat1622float2(h2);
-          const __nv_bfloat162 l2 = __floats2bfloat162_rn(y[2 * j] - f.x, y[2 * j + 1] - f.y);
-          lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+        for (int j = 0; j < 32; ++j) {
+          float t = __uint_as_float(v[j]);
+          if (p.bias) t += __ldg(p.bias + n + j);
+          y[j] = apply_act(t, p.act);
         }
-        uint4* qh = reinterpret_cast<uint4*>(p.out_hi + o);
+        const size_t o = (size_t)row * p.N + n;
+        if (p.out_f32) {
+          float4* q = reinterpret_cast<float4*>(p.out_f32 + o);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) qh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-        if (p.out_lo) {
-          uint4* ql = reinterpret_cast<uint4*>(p.out_lo + o);
+          for (int j = 0; j < 8; ++j) q[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+        }
+        if (p.out_hi) {
+          uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) ql[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          for (int j = 0; j < 16; ++j) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+            hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            const float2 f = __bfloat1622float2(h2);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(y[2 * j] - f.x, y[2 * j + 1] - f.y);
+            lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+          uint4* qh = reinterpret_cast<uint4*>(p.out_hi + o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) qh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          if (p.out_lo) {
+            uint4* ql = reinterpret_cast<uint4*>(p.out_lo + o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ql[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_accempty(buf));
     }
   }
   tc_fence_before();
@@ -267,14 +304,28 @@ static bool make_map(CUtensorMap* map, const void* base, int64_t rows, int K, in
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN>
+template <int BN, int kStages>
 static cudaError_t launch(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
                           const Params& p, cudaStream_t stream) {
-  constexpr int smem = kStages * (kABytes + BN * BK * 2) + 8 * (2 * kStages + 1) + 16 + 1024;  // + alignment slack
-  cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  constexpr int smem = kStages * (kABytes + BN * BK * 2) + 8 * (2 * kStages + 4) + 16 + 1024;  // + alignment slack
+  cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)((p.N + BN - 1) / BN));
-  gemm_kernel<BN><<<grid, kThreads, smem, stream>>>(a0, a1, b0, b1, p);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        sms <= 0)
+      sms = 148;
+  }
+  // CTAs per SM: limited by shared memory and by the 512 TMEM columns (two accumulators per CTA)
+  constexpr int tmem_cols = 2 * BN <= 256 ? 256 : 512;
+  int per_sm = (227 * 1024) / smem;
+  if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
+  if (per_sm < 1) per_sm = 1;
+  const long tiles = (long)((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  long grid = (long)sms * per_sm;
+  if (grid > tiles) grid = tiles;
+  gemm_kernel<BN, kStages><<<(unsigned)grid, threads(BN), smem, stream>>>(a0, a1, b0, b1, p);
   return cudaGetLastError();
 }
 
@@ -320,7 +371,10 @@ extern "C" int pmnet_gemm_bf16(const void* a_hi, const void* a_lo, const void* w
   p.out_hi = (__nv_bfloat16*)out_hi;
   p.out_lo = (__nv_bfloat16*)out_lo;
   p.act = act;
-  const cudaError_t e = BN == 192 ? launch<192>(a0, a1, b0, b1, p, stream) : launch<96>(a0, a1, b0, b1, p, stream);
+  const bool short_k = ((K + BK - 1) / BK) * p.npass <= 8;
+  cudaError_t e;
+  if (BN == 192) e = short_k ? launch<192, 2>(a0, a1, b0, b1, p, stream) : launch<192, 4>(a0, a1, b0, b1, p, stream);
+  else e = short_k ? launch<96, 2>(a0, a1, b0, b1, p, stream) : launch<96, 4>(a0, a1, b0, b1, p, stream);
   if (e != cudaSuccess) {
     pmnet_set_error(cudaGetErrorString(e));
     return PMNET_ECUDA;

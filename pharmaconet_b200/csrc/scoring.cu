@@ -1184,7 +1184,9 @@ bool use_fast_kernel(const PmScoreConfig* in, int n_nodes, int n_clusters, int n
   return fastk::smem_bytes(n_nodes, n_clusters, n_cluster_nodes) <= fastk::kSmemMax;
 }
 
-size_t fast_workspace_bytes() { return kHeaderBytes + (size_t)sm_count_cached() * fastk::kWarps * fastk::G_BYTES; }
+size_t fast_workspace_bytes() {
+  return kHeaderBytes + (size_t)sm_count_cached() * fastk::kCtasPerSm * fastk::kWarps * fastk::G_BYTES;
+}
 
 }  // namespace
 
@@ -1297,7 +1299,7 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
       set_err(cudaGetErrorString(e));
       return PMNET_ECUDA;
     }
-    fastk::pmnet_score_fast_kernel<<<sm_count_cached(), fastk::kWarps * 32, fsmem, stream>>>(fa);
+    fastk::pmnet_score_fast_kernel<<<sm_count_cached() * fastk::kCtasPerSm, fastk::kWarps * 32, fsmem, stream>>>(fa);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_err(cudaGetErrorString(e));

@@ -8,7 +8,7 @@ G = os.path.join(ROOT, "tests", "golden")
 man = json.load(open(os.path.join(G, "cnn_manifest.json")))
 buf = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, "cnn_buffers.npz")).items()}
 model = cnn.PharmacoNetModel(cnn_weights.synth_state_dict(man, buf, 0), "cuda:0")
-model.backbone.precision = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+model.precision = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 what = sys.argv[2] if len(sys.argv) > 2 else "backbone"
 x = torch.rand((8, 33, 64, 64, 64), device="cuda")
 fn = (lambda: model.backbone.forward(x)) if what == "backbone" else (lambda: model.forward_feature(x))

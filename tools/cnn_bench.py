@@ -21,6 +21,7 @@ ap.add_argument("--chunk", type=int, default=8, help="pockets per forward call")
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--groups", type=int, default=8, help="hotspot groups (of 4) for the mask-head timing")
 ap.add_argument("--torch-baseline", action="store_true")
+ap.add_argument("--reference", action="store_true", help="also time the unmodified reference modules (oracle/_ref) on this GPU")
 a = ap.parse_args()
 G = os.path.join(ROOT, "tests", "golden")
 man = json.load(open(os.path.join(G, "cnn_manifest.json")))
@@ -54,17 +55,17 @@ def stage_times():
     return out, feats
 
 
-for prec in ("fp32", "bf16"):
-    model.backbone.precision = prec
+for prec in ("bf16x3", "bf16"):
+    model.precision = prec
     t, feats = stage_times()
     n_chunks = a.batch // a.chunk
     per_pocket = (t["forward_feature"] + t["cavity"] + t["token"]) / a.chunk
     flop = 479.9e9
-    print(f"[backbone {prec}] per chunk of {a.chunk}: " + ", ".join(f"{k} {v:.2f} ms" for k, v in t.items()))
-    print(f"[backbone {prec}] pocket forward (feature+cavity+token): {per_pocket:.3f} ms/pocket, "
+    print(f"[{prec}] per chunk of {a.chunk}: " + ", ".join(f"{k} {v:.2f} ms" for k, v in t.items()))
+    print(f"[{prec}] pocket forward (feature+cavity+token): {per_pocket:.3f} ms/pocket, "
           f"{flop/per_pocket/1e9:.1f} TFLOP/s algorithmic; batch {a.batch}: {per_pocket*a.batch:.1f} ms")
     conv_ms = t["forward_feature"] - t["backbone"]
-    print(f"[backbone {prec}] FPN decoder share: {conv_ms/a.chunk:.3f} ms/pocket ({170.0e9/(conv_ms/a.chunk)/1e9:.1f} TFLOP/s), "
+    print(f"[{prec}] FPN decoder share: {conv_ms/a.chunk:.3f} ms/pocket ({170.0e9/(conv_ms/a.chunk)/1e9:.1f} TFLOP/s), "
           f"cavity {t['cavity']/a.chunk:.3f} ms/pocket ({261.0e9/(t['cavity']/a.chunk)/1e9:.1f} TFLOP/s)")
 
 _, tfeat = model.forward_token_prediction(feats[-1], [tokens] * a.chunk)
@@ -100,3 +101,26 @@ if a.torch_baseline:
     flop = 2.0 * a.chunk * 64**3 * 96 * 96 * 27
     print(f"torch conv3d+BN+ReLU 96->96 @64^3 x{a.chunk}: fp32/TF32 NCDHW {f32:.2f} ms ({flop/f32/1e9:.0f} TFLOP/s), "
           f"bf16 channels_last_3d {bf:.2f} ms ({flop/bf/1e9:.0f} TFLOP/s)")
+
+if a.reference:
+    # the reference's own nn.Modules through torch / cuDNN on the same GPU (the bar to beat)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_harness
+
+    ref_harness.import_reference()
+    from pmnet.network import build_model
+
+    ref = build_model({}).eval()
+    ref.load_state_dict(sd, strict=True)
+    ref = ref.cuda()
+    with torch.no_grad():
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            rf = ref.forward_feature(images)
+            t_feat = timed(lambda: ref.forward_feature(images), a.iters)
+            t_cav = timed(lambda: ref.forward_cavity_extraction(rf[-1]), a.iters)
+            t_tok = timed(lambda: ref.forward_token_prediction(rf[-1], [tokens] * a.chunk), a.iters)
+            per = (t_feat + t_cav + t_tok) / a.chunk
+            print(f"[reference modules on this GPU, tf32={tf32}] per chunk of {a.chunk}: forward_feature {t_feat:.2f} ms, cavity "
+                  f"{t_cav:.2f} ms, token {t_tok:.2f} ms -> {per:.3f} ms/pocket ({479.9e9/per/1e9:.1f} TFLOP/s algorithmic)")
