@@ -62,6 +62,11 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cnn", action="store_true", help="skip the CNN forward leg (BASELINE configs[3])")
+    ap.add_argument("--workload", default="screen", choices=["screen", "e2e"],
+                    help="screen = BASELINE configs[1] (the headline); e2e = configs[4]: pockets -> models -> screening")
+    ap.add_argument("--pockets-per-gpu", type=int, default=16, help="e2e: synthetic pockets per GPU (128 on 8 GPUs)")
+    ap.add_argument("--e2e-ligands", type=int, default=131072, help="e2e: ligands per GPU")
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16", "bf16x3"], help="e2e: CNN precision mode")
     return ap.parse_args()
 
 
@@ -434,6 +439,87 @@ def run_reference_port(args, world):
     print(json.dumps(line), flush=True)
 
 
+def run_e2e(args, rank, local_rank, world):
+    """BASELINE configs[4]: P synthetic pockets (P = pockets_per_gpu x N) through the CNN + model construction on their
+    owner rank, one all-gather of the packed models, every rank screens its resident ligand shard against all models,
+    one all-gather of the per-model top-k. Synthetic network weights (no trained checkpoint offline): the models are
+    structurally realistic only; what is measured is throughput, stage by stage."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from pharmaconet_b200 import cnn_weights, pipeline, synthetic
+    from pharmaconet_b200.module import PharmacoNet
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(dev)
+
+    G = os.path.join(ROOT, "tests", "golden")
+    with open(os.path.join(G, "cnn_manifest.json")) as f:
+        man = json.load(f)
+    buf = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, "cnn_buffers.npz")).items()}
+    net = PharmacoNet(dev, verbose=False, checkpoint=cnn_weights.synth_checkpoint(man, buf, 0), precision=args.precision)
+    gold = np.load(os.path.join(G, "cnn_pipeline_golden.npz"))
+    tokens = torch.from_numpy(gold["tokens"]).long()
+    token_pos = (tokens[:, :3].float() - 31.5) * 0.5
+    n_pockets = args.pockets_per_gpu * world
+    data = []
+    for p in range(n_pockets):  # every rank describes all pockets; only its own are materialised as tensors
+        if p % world == rank:
+            image = torch.rand((33, 64, 64, 64), generator=torch.Generator().manual_seed(p))
+            mask = torch.rand((64, 64, 64), generator=torch.Generator().manual_seed(1000 + p)) < 0.8
+            data.append((image, mask, token_pos, tokens))
+        else:
+            data.append(None)
+    shard = synthetic.make_library_device(args.e2e_ligands, args.conformers, args.seed + rank, dev, args.templates)
+    id_base = rank * args.e2e_ligands
+    for _ in range(max(1, min(args.warmup, 1))):
+        res = pipeline.model_and_screen(net, data, shard, id_base, args.topk, rank, world)
+    barrier()
+    t0 = time.perf_counter()
+    stages = {"modeling": 0.0, "exchange": 0.0, "screening": 0.0}
+    for _ in range(args.steps):
+        res = pipeline.model_and_screen(net, data, shard, id_base, args.topk, rank, world)
+        for k in stages:
+            stages[k] += res.seconds[k]
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    live = sum(m is not None for m in res.models)
+    pairs = live * world * shard.n_conformers_total * args.steps
+    if rank == 0:
+        nodes = [m.num_nodes for m in res.models if m is not None]
+        line = {
+            "metric": "pocket_ligand_conformer_pairs_scored_per_sec", "value": pairs / dt, "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": 1, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 scoring, " + args.precision + " CNN", "data": "synthetic",
+            "config": {
+                "workload": f"{n_pockets} synthetic 64^3 pockets -> pharmacophore models -> each against {args.e2e_ligands} "
+                            f"ligands x {args.conformers} conformers per GPU (BASELINE configs[4] shape)",
+                "pockets": n_pockets, "models_with_nodes": live, "model_nodes_mean": float(np.mean(nodes)) if nodes else 0.0,
+                "ligands_per_gpu": args.e2e_ligands, "parallelism": f"pockets p -> rank p mod {world}; ligand shards x{world}; "
+                "two small all-gathers (packed models, per-model top-k)",
+            },
+            "stage_seconds_per_step_rank0": {k: v / args.steps for k, v in stages.items()},
+            "pockets_per_sec": n_pockets * args.steps / dt, "n_overflow_rerun": res.n_overflow,
+        }  # fmt: skip
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -441,6 +527,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "e2e":
+        run_e2e(args, rank, local_rank, world)
         return
 
     import numpy as np

@@ -110,8 +110,21 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
          (2ull << 61);
 }
 
+// erf to 1.5e-7 absolute (Abramowitz & Stegun 7.1.26): one reciprocal, one exponential and five FMAs instead of the
+// branchy library erff - the epilogue of the fc1 GEMMs is bound by instruction issue, not by the tensor pipe
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float r = 1.0f - poly * t * __expf(-ax * ax);
+  return copysignf(r, x);
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == 1) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));  // nn.GELU (swin.py:32)
+  if (act == 1) return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752440f));  // nn.GELU (swin.py:32)
   if (act == 2) return fmaxf(x, 0.0f);
   if (act == 3) return x / (1.0f + __expf(-x));
   return x;
@@ -231,11 +244,23 @@ __global__ void __launch_bounds__(threads(BN)) gemm_kernel(const __grid_constant
         const int n = n0 + c32 * 32;
         if (!row_ok || n >= p.N) continue;
         float y[32];
+        if (p.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = __uint_as_float(v[j]);
-          if (p.bias) t += __ldg(p.bias + n + j);
-          y[j] = apply_act(t, p.act);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            y[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+            y[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+            y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+            y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]);
+        }
+        if (p.act) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = apply_act(y[j], p.act);
         }
         const size_t o = (size_t)row * p.N + n;
         if (p.out_f32) {
@@ -244,22 +269,25 @@ __global__ void __launch_bounds__(threads(BN)) gemm_kernel(const __grid_constant
           for (int j = 0; j < 8; ++j) q[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
         }
         if (p.out_hi) {
-          uint32_t hi[16], lo[16];
+          uint32_t hi[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const __nv_bfloat162 h2 = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
             hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
-            const float2 f = __bfloat1622float2(h2);
-            const __nv_bfloat162 l2 = __floats2bfloat162_rn(y[2 * j] - f.x, y[2 * j + 1] - f.y);
-            lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
           }
           uint4* qh = reinterpret_cast<uint4*>(p.out_hi + o);
 #pragma unroll
           for (int j = 0; j < 4; ++j) qh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-          if (p.out_lo) {
+          if (p.out_lo) {  // the residual of the bf16 rounding: the low operand of the next layer
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi[j]));
+              const __nv_bfloat162 l2 = __floats2bfloat162_rn(y[2 * j] - f.x, y[2 * j + 1] - f.y);
+              hi[j] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
             uint4* ql = reinterpret_cast<uint4*>(p.out_lo + o);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ql[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) ql[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
           }
         }
       }

@@ -77,12 +77,15 @@ class SwinV2Backbone:
     def _rel_bias(self, blk: str, heads: int, n: int) -> torch.Tensor:
         """16 * sigmoid(cpb_mlp(relative_coords_table))[relative_position_index] -> [heads, n, n]; input independent."""
         if blk not in self._bias_cache:
-            table = self._g(blk + "attn.relative_coords_table")
-            h = F.relu(F.linear(table, self._g(blk + "attn.cpb_mlp.0.weight"), self._g(blk + "attn.cpb_mlp.0.bias")))
-            t = F.linear(h, self._g(blk + "attn.cpb_mlp.2.weight")).view(-1, heads)
-            idx = self._g(blk + "attn.relative_position_index").view(-1)
+            # input independent (a 343 x 3 table through a 3 -> 512 -> heads MLP): evaluated ONCE on the host when the
+            # block is first used, then kept on the device - no library GEMM on the forward path
+            dev = self._g(blk + "attn.relative_coords_table").device
+            c = lambda name: self._g(blk + name).detach().float().cpu()  # noqa: E731
+            h = F.relu(F.linear(c("attn.relative_coords_table"), c("attn.cpb_mlp.0.weight"), c("attn.cpb_mlp.0.bias")))
+            t = F.linear(h, c("attn.cpb_mlp.2.weight")).view(-1, heads)
+            idx = self._g(blk + "attn.relative_position_index").view(-1).cpu()
             bias = t[idx].view(n, n, heads).permute(2, 0, 1).contiguous()
-            self._bias_cache[blk] = 16.0 * torch.sigmoid(bias)
+            self._bias_cache[blk] = (16.0 * torch.sigmoid(bias)).to(dev)
         return self._bias_cache[blk]
 
     def _attention(self, xw: torch.Tensor, blk: str, heads: int, mask: torch.Tensor | None) -> torch.Tensor:

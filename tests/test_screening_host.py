@@ -89,3 +89,44 @@ def test_numa_binding_is_a_noop_without_nvml():
     else:  # a GPU box: bound to a non-empty subset of what was allowed
         assert set(cpus) <= before and len(cpus) > 0
         os.sched_setaffinity(0, before)
+
+
+def _pipeline_worker(rank, world, port, out_dir):
+    from pharmaconet_b200 import pipeline
+    from pharmaconet_b200.packing import PackedModel
+    from pharmaconet_b200.pharmacophore_model import PharmacophoreModel
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    names = ["syn0", "loose", "sparse", "xbond", "syn0"]  # 5 "pockets": rank r builds pockets r, r + 2, ...
+    local = {
+        p: PackedModel.from_model(PharmacophoreModel.load(os.path.join(golden, f"model_{names[p]}.pm")))
+        for p in pipeline.pockets_of_rank(len(names), rank, world)
+    }
+    models = pipeline.exchange_models(local, len(names))
+    torch.save([m.arrays() for m in models], os.path.join(out_dir, f"m{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_pipeline_model_exchange_world2(tmp_path):
+    """configs[4]: the packed pharmacophore models built on different ranks reach every rank, in pocket order."""
+    from pharmaconet_b200 import pipeline
+    from pharmaconet_b200.packing import PackedModel
+    from pharmaconet_b200.pharmacophore_model import PharmacophoreModel
+
+    assert pipeline.pockets_of_rank(5, 0, 2) == [0, 2, 4] and pipeline.pockets_of_rank(5, 1, 2) == [1, 3]
+    port = _free_port()
+    mp.spawn(_pipeline_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = torch.load(os.path.join(tmp_path, "m0.pt"), weights_only=False)
+    b = torch.load(os.path.join(tmp_path, "m1.pt"), weights_only=False)
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    names = ["syn0", "loose", "sparse", "xbond", "syn0"]
+    for p, name in enumerate(names):
+        ref = PackedModel.from_model(PharmacophoreModel.load(os.path.join(golden, f"model_{name}.pm"))).arrays()
+        for k, v in ref.items():
+            assert np.array_equal(a[p][k], v) and np.array_equal(b[p][k], v), (p, k)
+    # single process: no collective, same result
+    local = {p: PackedModel.from_arrays(a[p]) for p in range(5)}
+    solo = pipeline.exchange_models(local, 5)
+    assert all(np.array_equal(solo[p].arrays()["edge_mu"], a[p]["edge_mu"]) for p in range(5))
