@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cnn", action="store_true", help="skip the CNN forward leg (BASELINE configs[3])")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-model scoring leg")
     ap.add_argument("--workload", default="screen", choices=["screen", "e2e"],
                     help="screen = BASELINE configs[1] (the headline); e2e = configs[4]: pockets -> models -> screening")
     ap.add_argument("--pockets-per-gpu", type=int, default=16, help="e2e: synthetic pockets per GPU (128 on 8 GPUs)")
@@ -281,6 +282,44 @@ def cnn_forward_leg(dev, batch: int = 64, chunk: int = 8, iters: int = 2):
         out["reference_modules_same_gpu"] = {"error": repr(e)}
     torch.cuda.empty_cache()
     return out
+
+
+def dense_model_leg(lib, dev, args, n_ligands: int = 131072, hotspots: int = 60):
+    """Second scoring workload: a synthetic model of the size the CNN produces for hotspot-rich pockets (about 50
+    nodes / 40 clusters instead of the headline's 35 / 26): trees are an order of magnitude larger, more ligands exceed
+    the specialised kernel's caps and some overflow the default scratch (re-run in place)."""
+    import torch
+
+    from pharmaconet_b200 import scoring, screening, synthetic
+    from pharmaconet_b200.pharmacophore_model import PharmacophoreModel
+
+    model = PharmacophoreModel.create("", (0.0, 0.0, 0.0), synthetic.make_hotspot_infos(seed=21, n_hotspots=hotspots))
+    n = min(n_ligands, lib.n_ligands)
+    sub = scoring.DeviceLigandBatch(lib.tensors, n, n * args.conformers, max_conformers=lib.max_conformers)
+    scr = screening.Screener(model.packed, dev, k=args.topk)
+    out = scoring.score_batch(scr.model, sub, with_stats=True)
+    st = out["status"]
+    stats = out["stats"].cpu().numpy().view("uint32")
+    deferred_or_over = int((st == 2).sum().item())
+    scr.screen_device(sub)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 2
+    e0.record()
+    for _ in range(iters):
+        sub.set_order(None)
+        res = scr.screen_device(sub, gather=False)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    return {
+        "workload": f"synthetic dense model ({len(model.nodes)} nodes / {len(model.node_clusters)} clusters, {hotspots} hotspots) x "
+                    f"first {n} ligands x {args.conformers} conformers of the same library, resident",
+        "value": n * args.conformers / (ms * 1e-3), "unit": UNIT, "ms_per_pass": ms,
+        "tree_nodes_mean": float(stats[:, 0].mean()), "tree_nodes_max": int(stats[:, 0].max()),
+        "pair_entries_mean": float(stats[:, 3].mean()), "overflowed_default_scratch": deferred_or_over,
+        "n_overflow_rerun": res.n_overflow,
+    }  # fmt: skip
 
 
 def host_prefix(dev_lib, n):
@@ -612,6 +651,14 @@ def main():
     gpu_scores = res.scores  # device tensor, this rank
     top_ids = res.topk_ids.cpu().numpy()
 
+    # ---------------------------------------------------------------- leg 1b: a denser, CNN-sized model (rank 0, N = 1)
+    dense = None
+    if rank == 0 and world == 1 and not args.no_dense:
+        try:
+            dense = dense_model_leg(lib, dev, args)
+        except Exception as e:  # noqa: BLE001 - the headline metric must still be printed
+            dense = {"error": repr(e)}
+
     # ---------------------------------------------------------------- leg 2: end to end from pinned host memory
     e2e = None
     if not args.no_e2e:
@@ -747,6 +794,7 @@ def main():
                         "is reported because BASELINE.json asks for it",
             },
             "issue_roofline": issue,
+            "dense_model": dense,
             "cnn_conv3d_roofline": conv_roofline,
             "cnn_forward": cnn_forward,
             "cpu_baseline": cpu_baseline, "cpu_port": cpu_port, "parity": parity, "clocks": clocks,
