@@ -11,8 +11,11 @@ from __future__ import annotations
 import os
 
 
-def bind_to_gpu(gpu_index: int) -> list[int] | None:
-    """Restrict this process to the CPUs local to `gpu_index`. Returns the CPU list, or None if nothing was done."""
+def bind_to_gpu(gpu_index: int, world: int = 1) -> list[int] | None:
+    """Restrict this process to the CPUs local to `gpu_index`. Returns the CPU list, or None if nothing was done.
+    When NVML reports no locality (a VM without NUMA information: every CPU is "local" to every GPU) and `world` > 1,
+    the allowed CPUs are cut into `world` equal slices and rank `gpu_index` takes its own, so that the ranks' copy /
+    launch threads at least do not share cores."""
     try:
         import pynvml
 
@@ -27,7 +30,11 @@ def bind_to_gpu(gpu_index: int) -> list[int] | None:
         allowed = os.sched_getaffinity(0)
         cpus = [c for c in cpus if c in allowed]
         if not cpus or len(cpus) == len(allowed):
-            return None
+            if world <= 1 or len(allowed) < world:
+                return None
+            ordered = sorted(allowed)
+            per = len(ordered) // world
+            cpus = ordered[(gpu_index % world) * per : (gpu_index % world + 1) * per]
         os.sched_setaffinity(0, cpus)
         return cpus
     except Exception:  # noqa: BLE001 - placement is an optimisation, never a failure
