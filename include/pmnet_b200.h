@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PMNET_ABI_VERSION 3
+#define PMNET_ABI_VERSION 4
 
 /* pharmacophore types, bit positions of every type mask (graph_match.py:32-40) */
 enum {
@@ -56,8 +56,10 @@ enum {
   PMNET_LIG_EMPTY = 1,    /* no cluster / no candidate: score 0 (graph_match.py:95-99), not an error */
   PMNET_LIG_OVERFLOW = 2, /* per-warp scratch exhausted: score not computed; re-run with a larger scratch */
   PMNET_LIG_UNSUPPORTED = 3, /* more conformers than PMNET_MAX_CONFORMERS */
-  PMNET_LIG_DEFERRED = 4     /* internal: left by the specialised kernel for the general kernel that pmnet_score_batch
+  PMNET_LIG_DEFERRED = 4,    /* internal: left by the specialised kernel for the general kernel that pmnet_score_batch
                                 enqueues behind it in the same call; never visible once the stream has drained */
+  PMNET_LIG_HEAVY = 5        /* internal: the tree outgrew PmScoreConfig.heavy_budget and was handed to the task-parallel
+                                walk of the same call; never visible once the stream has drained */
 };
 
 #define PMNET_MAX_CONFORMERS 128  /* one warp lane per conformer, up to 4 conformers per lane */
@@ -122,7 +124,11 @@ typedef struct PmScoreConfig {
                                 this PMNET_LIG_* code are scored (the others keep score and status): re-running the
                                 PMNET_LIG_OVERFLOW ligands of a previous call with a larger scratch needs no host copy
                                 of the library and no compaction */
-  int32_t reserved[3];
+  int32_t heavy_budget;      /* tree nodes after which one warp stops walking a ligand and the same call splits its tree
+                                over many warps (one task per pair of level-0 / level-1 entries); 0: default 262144,
+                                < 0: never split. Only with max_conformers <= 32 and rescore_status == 0. Scores,
+                                per-conformer scores and tree statistics do not depend on it */
+  int32_t reserved[2];
 } PmScoreConfig;
 
 int pmnet_abi_version(void);
@@ -143,6 +149,9 @@ size_t pmnet_score_workspace_bytes(int32_t n_model_nodes, int32_t n_model_cluste
  * per-ligand tables in shared memory; csrc/scoring_fast.cuh) and, behind it, the general one for the ligands the first
  * left PMNET_LIG_DEFERRED. Both compute the same fp32 operations in the same order: results do not depend on which one
  * scored a ligand. An explicit warps_per_block / blocks / scratch_rows selects the general kernel alone.
+ * Unless heavy_budget < 0, three more (normally empty) launches follow: the task kernel that walks the trees larger
+ * than heavy_budget with one warp per (level-0 entry, level-1 entry) subtree, the kernel that merges the task records,
+ * and the general kernel once more for heavy ligands whose tree cannot be split that way.
  */
 int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const float* weights,
                       float* out_scores, float* out_conf_scores, int32_t* out_status, uint32_t* out_stats,

@@ -4,10 +4,10 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 PMNET_OK, PMNET_EINVAL, PMNET_EWORKSPACE, PMNET_ELIMIT, PMNET_ECUDA = range(5)
-LIG_OK, LIG_EMPTY, LIG_OVERFLOW, LIG_UNSUPPORTED, LIG_DEFERRED = range(5)
+LIG_OK, LIG_EMPTY, LIG_OVERFLOW, LIG_UNSUPPORTED, LIG_DEFERRED, LIG_HEAVY = range(6)
 MAX_CONFORMERS = 128
 
 _u8p = C.POINTER(C.c_uint8)
@@ -60,7 +60,8 @@ class PmScoreConfig(C.Structure):
         ("scratch_rows", C.c_int32),
         ("max_conformers", C.c_int32),
         ("rescore_status", C.c_int32),
-        ("reserved", C.c_int32 * 3),
+        ("heavy_budget", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
 

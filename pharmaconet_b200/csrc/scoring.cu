@@ -98,6 +98,52 @@ __host__ __device__ inline WarpLayout make_layout(int n_model_clusters, int scra
 }
 
 constexpr size_t kHeaderBytes = 256;
+// header words: [0] queue of the specialised kernel, [1] number of heavy ligands, [2] queue of the general kernel
+// (deferred pass), [3] queue of the task kernel, [4] queue of the general kernel (last pass: what could not be split),
+// [5] number of deferred ligands, [6] queue of the task kernel's second pass, [7] N(e0) tasks requested for it,
+// [8] heavy ligands left to the un-split last pass (7 and 8: diagnostics, read by the tests)
+
+// ---------------------------------------------------------------- heavy ligands (task-parallel DFS)
+// A ligand whose tree exceeds `heavy_budget` nodes is abandoned (status PMNET_LIG_HEAVY) and appended to a list; its
+// tree is then walked by MANY warps: task (e0, e1) = the subtree below the matched level-0 entry e0 and the matched
+// level-1 entry e1, task N(e0) = the subtree below e0's None child. Every task warp recomputes phases 0-1 (cheap next
+// to a tree of 10^5+ nodes), walks its subtree with the prefix forced, leaves a 4-word record and folds its
+// per-conformer best scores into the ligand's accumulator (an integer atomicMax on non-negative floats: exact and
+// order independent). pmnet_heavy_combine_kernel merges the records of a ligand following tree.py:93-102:
+//   pass 1: the (e0, e1) tasks, and N(e0) where e0 has no level-1 candidate (its None child exists for sure). An e0
+//           whose children returned fewer than 4 matches also has a None child: those are requested in a bit mask
+//   pass 2: the requested N(e0) tasks, then the merge of everything
+// A ligand whose ROOT needs a None child (no path with 5 matches - not seen on trees this large) or that cannot be
+// split (fewer than 3 levels, a level 0 / 1 of more than 32 entries) keeps PMNET_LIG_HEAVY and is walked un-split by
+// the last launch. Scores, per-conformer scores and tree statistics are identical to the un-split walk.
+constexpr int kHeavyCap = 4096;           // heavy ligands split per call (more are walked to the end where they are)
+constexpr int kTaskSlots = 32 * 32 + 32;  // (e0, e1) tasks + N(e0) tasks per heavy ligand
+constexpr int kTaskRecWords = 4;          // flags (bit 0 exists, bit 1 cannot split) | K0 << 8 | K1 << 16, ret, nodes, leaves
+constexpr int kAccWords = 40;             // per heavy ligand: best[32], rows, pairs, requested N(e0) mask, -
+constexpr int kAccRows = 32, kAccPairs = 33, kAccNeed = 34;
+constexpr size_t kHeavyBytes =
+    ((size_t)kHeavyCap * 4 * (1 + kAccWords + (size_t)kTaskSlots * kTaskRecWords) + 255) / 256 * 256;
+constexpr uint32_t kDefaultHeavyBudget = 1u << 17;
+
+// Claim a slot of the heavy list for `lig` (whole warp; false: the list is full) and clear its accumulator.
+__device__ __forceinline__ bool heavy_append(unsigned char* workspace, uint32_t* heavy_list, uint32_t* heavy_acc,
+                                             uint32_t lig, int lane) {
+  unsigned hi = 0;
+  if (lane == 0) hi = atomicAdd((unsigned int*)workspace + 1, 1u);
+  hi = __shfl_sync(0xffffffffu, hi, 0);
+  if (hi >= (unsigned)kHeavyCap) return false;
+  if (lane == 0) heavy_list[hi] = lig;
+  uint32_t* acc = heavy_acc + (size_t)hi * kAccWords;
+  acc[lane] = 0u;
+  if (lane < kAccWords - 32) acc[32 + lane] = 0u;
+  return true;
+}
+
+// Ligands the specialised kernel defers are appended to a list (when the call has at most this many ligands) so that
+// the general kernel hands them out one at a time in the same longest-first order; a larger call falls back to the
+// status scan (32 queue positions per warp), which is only balanced when deferred ligands are sparse.
+constexpr int kDeferCap = 1 << 20;
+constexpr size_t kDeferBytes = (size_t)kDeferCap * 4;
 
 // ---------------------------------------------------------------- shared-memory model image
 struct SmemModel {
@@ -166,6 +212,14 @@ struct KernelArgs {
   int conf_stride;  // floats per ligand in out_conf (32 * W)
   int only_status;  // -1: score every ligand; else only the ligands whose out_status holds this code (deferred / re-run)
   int counter_word; // 32-bit word of the workspace header that is this launch's queue counter
+  const uint32_t* list;  // non-null: the queue runs over this list of ligands (only_status still filters)
+  int list_count_word;   // header word holding the list's length
+  int list_cap;
+  uint32_t heavy_budget;   // tree nodes after which a ligand is abandoned as PMNET_LIG_HEAVY (0: never)
+  uint32_t* heavy_list;    // [kHeavyCap] ligand indices (count in header word 1)
+  uint32_t* heavy_acc;     // [kHeavyCap][kAccWords]
+  uint32_t* task_rec;      // [kHeavyCap][kTaskSlots][kTaskRecWords]
+  int task_pass;           // task kernel: 1 = (e0, e1) tasks + N(e0) of entries without level-1 candidates, 2 = requested N(e0)
   WarpLayout ly;    // computed once on the host: the kernel reads the offsets from the constant bank
   const float4* edge_g;  // large models: the edge table in the workspace (build_edge_table_kernel)
 };
@@ -304,7 +358,8 @@ __global__ void build_edge_table_kernel(const EdgeTableArgs a) {
 
 #include "scoring_fast.cuh"
 
-template <int W, bool TG>
+// TK = task kernel: the queue runs over (heavy ligand, task slot) pairs and the DFS walks one forced prefix.
+template <int W, bool TG, bool TK = false>
 __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_kernel(const KernelArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int CW = 32 * W;  // conformer slots per row
@@ -387,7 +442,52 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
   unsigned pend_lig = 0;
   for (;;) {
     unsigned int lig = 0;
-    if (args.only_status < 0) {
+    int task_e0 = 0, task_e1 = -1;  // TK: forced level-0 entry, forced level-1 entry (-1: the None child of e0)
+    uint32_t* task_out = nullptr;
+    uint32_t* task_acc = nullptr;
+    if (TK) {
+      unsigned t = 0;
+      if (lane == 0) t = atomicAdd(counter, 1u);
+      t = __shfl_sync(kFull, t, 0);
+      unsigned nh = ((const unsigned int*)args.workspace)[1];
+      if (nh > (unsigned)kHeavyCap) nh = kHeavyCap;
+      unsigned h, slot;
+      if (args.task_pass == 1) {
+        if (t >= nh * (unsigned)kTaskSlots) break;
+        h = t / kTaskSlots;
+        slot = t % kTaskSlots;
+      } else {
+        if (t >= nh * 32u) break;
+        h = t >> 5;
+        slot = 1024u + (t & 31u);
+        if (!((args.heavy_acc[(size_t)h * kAccWords + kAccNeed] >> (t & 31u)) & 1u)) continue;
+      }
+      lig = args.heavy_list[h];
+      if (slot < 1024u) {
+        task_e0 = (int)(slot >> 5);
+        task_e1 = (int)(slot & 31u);
+      } else {
+        task_e0 = (int)(slot - 1024u);
+      }
+      task_out = args.task_rec + ((size_t)h * kTaskSlots + slot) * kTaskRecWords;
+      task_acc = args.heavy_acc + (size_t)h * kAccWords;
+    } else if (args.list != nullptr) {
+      bool done = false;
+      for (;;) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(counter, 1u);
+        t = __shfl_sync(kFull, t, 0);
+        unsigned nl = ((const unsigned int*)args.workspace)[args.list_count_word];
+        if (nl > (unsigned)args.list_cap) nl = args.list_cap;
+        if (t >= nl) {
+          done = true;
+          break;
+        }
+        lig = args.list[t];
+        if (args.only_status < 0 || args.out_status[lig] == args.only_status) break;
+      }
+      if (done) break;
+    } else if (args.only_status < 0) {
       if (lane == 0) {
         lig = atomicAdd(counter, 1u);
         if (B.order != nullptr && lig < (unsigned)B.n_ligands) lig = (unsigned)B.order[lig];
@@ -422,12 +522,24 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
     float score_out = 0.0f;
     int status = PMNET_LIG_OK;
     uint32_t st_nodes = 0, st_leaves = 0, st_rows = 0, st_pairs = 0;
+#ifdef PM_TIMING
+    unsigned long long tm0 = 0, tm1 = 0, tm2 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm0));
+    tm1 = tm0;
+#endif
     float best[W];
 #pragma unroll
     for (int w = 0; w < W; ++w) best[w] = 0.0f;
+    bool task_skip = false;     // TK: this task does not exist for the ligand (or the ligand cannot be split)
+    bool task_exists = true;    // TK: cleared when the forced prefix turns out not to be part of the tree
+    unsigned task_flags = 0;    // TK: bit 1 = the ligand cannot be split, K0 << 8, K1 << 16
+    int task_ret = 0;           // TK: matches returned to the root (tree.py:100)
+    bool heavy = false;         // the tree exceeded the node budget: abandoned, to be split into tasks
+    bool heavy_denied = false;  // the list of heavy ligands is full: walk the tree to the end here
 
     if (C < 1 || C > CW) {
       status = PMNET_LIG_UNSUPPORTED;
+      task_flags |= 2u;
     } else {
       const int stride = (C + 3) & ~3;
       const float* xyz = B.coords + (B.coord_off[lig] - B.coord_base);
@@ -520,9 +632,20 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
       if (!overflow && L > 0) {
         if (lane == 0) ws.lev_start[L] = T;
         __syncwarp();
+        if (TK) {
+          const int K0 = ws.lev_start[1] - ws.lev_start[0];
+          const int K1 = L >= 2 ? ws.lev_start[2] - ws.lev_start[1] : 0;
+          task_flags = ((unsigned)K0 << 8) | ((unsigned)K1 << 16);
+          if (L < 3 || K0 > 32 || K1 > 32) {
+            task_flags |= 2u;  // cannot be split by (e0, e1) prefixes
+            task_skip = true;
+          } else if (task_e0 >= K0 || task_e1 >= K1) {
+            task_skip = true;
+          }
+        }
         // node-match records, one lane per entry: count, exclusive scan for the offsets, then fill
         uint32_t rec_used = 0, ml_used = 0;
-        for (int e0 = 0; e0 < T && !overflow; e0 += 32) {
+        for (int e0 = 0; e0 < T && !overflow && !task_skip; e0 += 32) {
           const int e = e0 + lane;
           uint32_t nrec = 0, nml = 0;
           bool toobig = false;
@@ -587,7 +710,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
           ml_used += tml;
         }
         // pair-index base of each entry: V/prow rows of e1 cover all entries of later levels
-        if (!overflow) {
+        if (!overflow && !task_skip) {
           int run = 0;  // running pair count, computed level by level (uniform)
           for (int l = 0; l < L; ++l) {
             const int s = ws.lev_start[l], e_end = ws.lev_start[l + 1];
@@ -604,7 +727,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
           if (run > LY.pair_cap) overflow = true;
         }
         // ligand node-pair distances (LigandEdge.set_distances, ligand.py:349-351), upper triangle of NL x NL
-        if (!overflow) {
+        if (!overflow && !task_skip) {
           for (int i = 0; i < NL - 1; ++i) {
             const int ni = lnode[i];
             float xi[W], yi[W], zi[W];
@@ -633,8 +756,12 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
 
       if (overflow) {
         status = PMNET_LIG_OVERFLOW;
+        task_flags |= 2u;
       } else if (L == 0) {
         status = PMNET_LIG_EMPTY;
+        task_flags |= 2u;
+      } else if (TK && task_skip) {
+        // nothing to walk
       } else {
         // ================= phase 1: self scores and pair table (graph_match.py:222-279)
         // (row / distance indices fit 32 bits: at most 2^17 rows and 255^2 node pairs of 128 conformer slots)
@@ -775,7 +902,11 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
 
         if (overflow) {
           status = PMNET_LIG_OVERFLOW;
+          task_flags |= 2u;
         } else {
+#ifdef PM_TIMING
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm1));
+#endif
           // ================= phase 2: DFS (tree.py:55-104) with an explicit stack; lane d holds depth d's state
           int st_cursor = 0, st_maxm = 0, st_nchild = 0, st_phase = 0, st_nmatch = 0, st_entry = -1, st_mslot = 0,
               st_tslot = 0, st_pbase = 0;
@@ -790,7 +921,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
             tot_l[32 * w] = 0.0f;
           }
           if (lane == 0) {
-            st_cursor = 0;  // lev_start[0]
+            st_cursor = TK ? task_e0 : 0;  // lev_start[0] (TK: the forced level-0 entry)
 #pragma unroll
             for (int w = 0; w < W; ++w) st_alive[w] = cfull[w];
           }
@@ -887,6 +1018,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
             } else if (phase == 0) {
               int cur = __shfl_sync(kFull, st_cursor, d);
               const int end = ws.lev_start[y + 1];
+              const bool first_visit = cur < end;
               int found = -1;
               unsigned alive2[W];
 #pragma unroll
@@ -910,11 +1042,24 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
                 }
                 cur += 32;
               }
+              if (TK && first_visit && ((d == 1 && task_e1 >= 0 && found != ws.lev_start[1] + task_e1) ||
+                                        (d == 0 && found != task_e0))) {
+                task_exists = false;  // the forced entry is not a candidate below its parent
+                break;
+              }
               if (found >= 0) {
                 // ---- matched child (y, found): ClusterMatchTree.__init__ (tree.py:33-41); it is not a leaf
                 ++st_nodes;
+                if (!TK && args.heavy_budget != 0u && st_nodes > args.heavy_budget && !heavy_denied) {
+                  // abandon: the tree is split into tasks (pmnet_score_batch) - if the list has room
+                  if (heavy_append(args.workspace, args.heavy_list, args.heavy_acc, lig, lane)) {
+                    heavy = true;
+                    break;
+                  }
+                  heavy_denied = true;
+                }
                 if (lane == d) {
-                  st_cursor = found + 1;
+                  st_cursor = (TK && d <= 1) ? end : found + 1;  // TK: the prefix nodes have exactly one child
                   st_nchild += 1;
                 }
                 // everything that depends only on `found` is requested first: the ancestors' pair-row indices,
@@ -962,6 +1107,10 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
 #pragma unroll
                   for (int w = 0; w < W; ++w) any0 |= pmv[w] & alive2[w] & vtv[w];
                   if (T - end <= 32 && !__any_sync(kFull, any0 != 0u)) {
+                    if (TK && d == 0 && task_e1 >= 0) {
+                      task_exists = false;  // e0 has no candidate below it: only its N(e0) task exists
+                      break;
+                    }
                     st_nodes += L - d - 1;
                     ++st_leaves;
 #pragma unroll
@@ -1042,6 +1191,23 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
                   if (lane == d) st_maxm = max(st_maxm, 2);  // the child returns 1 (a matched leaf) + 1 (itself)
                   continue;
                 }
+                int child_cursor = end;
+                if (TK && d == 0) {
+                  // does e0 have a level-1 candidate at all? (level 1 has at most 32 entries: all in this chunk)
+                  unsigned anyl1 = 0;
+#pragma unroll
+                  for (int w = 0; w < W; ++w) anyl1 |= pmv[w] & alive2[w] & vtv[w];
+                  const bool has_l1 = __any_sync(kFull, anyl1 != 0u && e2a < ws.lev_start[2]);
+                  if (task_e1 < 0) {
+                    if (has_l1 && args.task_pass == 1) {
+                      task_exists = false;  // pass 1 walks N(e0) only when e0 has no level-1 candidate
+                      break;
+                    }
+                    child_cursor = ws.lev_start[2];  // nothing to find: the None child follows (tree.py:98)
+                  } else {
+                    child_cursor = end + task_e1;
+                  }
+                }
                 // the child's candidate masks: parent mask & conformers alive in the child & pair validity.
                 // (depth d + 1's slot was last read by other lanes while the previous child's subtree was walked)
                 __syncwarp();
@@ -1057,7 +1223,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
 #pragma unroll
                 for (int w = 0; w < W; ++w) tot_l[(d + 1) * CW + 32 * w] = t[w] + acc[w];
                 if (lane == d + 1) {
-                  st_cursor = end;
+                  st_cursor = child_cursor;
                   st_maxm = 0;
                   st_nchild = 0;
                   st_phase = 0;
@@ -1077,7 +1243,10 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
               const int nchild = __shfl_sync(kFull, st_nchild, d);
               const int nmatch = __shfl_sync(kFull, st_nmatch, d);
               const int maxm = __shfl_sync(kFull, st_maxm, d);
-              if (nchild == 0 || nmatch + maxm < PMNET_MIN_MATCHES) {
+              // TK: the None children of the prefix nodes (the root, and e0 in an (e0, e1) task) are not this task's
+              // business - the combine step checks that the tree does not have them
+              const bool prefix_node = TK && (d == 0 || (d == 1 && task_e1 >= 0));
+              if (!prefix_node && (nchild == 0 || nmatch + maxm < PMNET_MIN_MATCHES)) {
                 // the None child is not a leaf here (y < L - 1): same masks and totals, one level down
                 ++st_nodes;
                 if (lane == d) st_phase = 1;
@@ -1111,6 +1280,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
               d = d - 1;
             }
           }
+          if (TK) task_ret = __shfl_sync(kFull, st_maxm, 0);
           // mean over conformers (graph_match.py:109)
           double s = 0.0;
 #pragma unroll
@@ -1121,6 +1291,30 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
       }
       (void)lane_on;
     }
+    if (TK) {
+      // the task's record (pmnet_heavy_combine_kernel); W == 1
+      const bool ex = task_exists && !task_skip && status == PMNET_LIG_OK && !(task_flags & 2u);
+      if (lane == 0) {
+        *(uint4*)task_out = make_uint4(task_flags | (ex ? 1u : 0u), (uint32_t)task_ret, st_nodes, st_leaves);
+        if (ex) {
+          task_acc[kAccRows] = st_rows;  // the same in every task of the ligand
+          task_acc[kAccPairs] = st_pairs;
+        }
+      }
+      // scores are >= 0 (best starts at 0): their bit patterns order like integers
+      if (ex) atomicMax((int*)task_acc + lane, __float_as_int(best[0]));
+      __syncwarp();
+      continue;
+    }
+    if (heavy) {
+      status = PMNET_LIG_HEAVY;
+      score_out = 0.0f;
+    }
+#ifdef PM_TIMING
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm2));
+    st_rows = (uint32_t)((tm1 - tm0) / 1000ull);
+    st_pairs = (uint32_t)((tm2 - tm1) / 1000ull);
+#endif
     if (lane == 0) {
       args.out_scores[lig] = score_out;
       args.out_status[lig] = status;
@@ -1142,6 +1336,112 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
   }
 }
 
+
+// One warp per heavy ligand: merge the task records into the ligand's score, statistics and status (see the notes
+// at kHeavyCap). pass 1 finishes the ligands that need no further N(e0) task and requests those tasks for the others;
+// pass 2 finishes the others.
+struct CombineArgs {
+  unsigned char* workspace;
+  const uint32_t* heavy_list;
+  uint32_t* heavy_acc;
+  const uint32_t* task_rec;
+  const int32_t* n_conf;
+  float* out_scores;
+  float* out_conf;
+  int32_t* out_status;
+  uint32_t* out_stats;
+  int conf_stride;
+  int pass;
+};
+
+__global__ void __launch_bounds__(128) pmnet_heavy_combine_kernel(const CombineArgs args) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  unsigned nh = ((const unsigned int*)args.workspace)[1];
+  if (nh > (unsigned)kHeavyCap) nh = kHeavyCap;
+  for (unsigned h = warp; h < nh; h += nwarps) {
+    const uint32_t lig = args.heavy_list[h];
+    uint32_t* const acc = args.heavy_acc + (size_t)h * kAccWords;
+    const uint4* const rec = (const uint4*)(args.task_rec + (size_t)h * kTaskSlots * kTaskRecWords);
+    const uint32_t requested = acc[kAccNeed];
+    if (args.pass == 2 && requested == 0u) continue;  // finished (or given up) in pass 1
+    const uint32_t f0 = rec[0].x;
+    bool ok = (f0 & 2u) == 0u;
+    const int K0 = (int)((f0 >> 8) & 255u), K1 = (int)((f0 >> 16) & 255u);
+    if (K0 < 1 || K0 > 32 || K1 < 1 || K1 > 32) ok = false;
+    uint32_t nodes = 1, leaves = 0, need = 0;
+    int max_root = 0;
+    for (int e0 = 0; e0 < K0 && ok; ++e0) {
+      const uint4 r = rec[e0 * 32 + lane];
+      const bool ex = lane < K1 && (r.x & 1u);
+      const unsigned bal = __ballot_sync(kFull, ex);
+      const uint4 rn = rec[1024 + e0];
+      const bool exn = (rn.x & 1u) != 0u;
+      const bool want_n = bal == 0u || ((requested >> e0) & 1u);  // N(e0) is part of the tree
+      if (exn != want_n) {
+        ok = false;  // not a tree this split describes
+        break;
+      }
+      int m = 0;  // most matches below e0
+      nodes += 1u;
+      if (bal) {
+        m = ex ? (int)r.y - 1 : 0;
+        uint32_t nn = ex ? r.z - 2u : 0u, nl = ex ? r.w : 0u;
+        for (int o = 16; o > 0; o >>= 1) {
+          m = max(m, __shfl_xor_sync(kFull, m, o));
+          nn += __shfl_xor_sync(kFull, nn, o);
+          nl += __shfl_xor_sync(kFull, nl, o);
+        }
+        nodes += nn;
+        leaves += nl;
+        // tree.py:98 at e0 (one match on the path): its children returned too few matches - a None child follows
+        if (1 + m < PMNET_MIN_MATCHES && !exn) need |= 1u << e0;
+      }
+      if (exn) {
+        m = max(m, (int)rn.y - 1);
+        nodes += rn.z - 2u;
+        leaves += rn.w;
+      }
+      max_root = max(max_root, 1 + m);
+    }
+    if (ok && need != 0u) {
+      if (args.pass == 1) {
+        if (lane == 0) {
+          acc[kAccNeed] = need;  // pass 2 walks these and comes back
+          atomicAdd((unsigned int*)args.workspace + 7, (unsigned)__popc(need));
+        }
+        continue;
+      }
+      ok = false;  // (cannot happen: pass 2 has walked every requested N(e0))
+    }
+    if (ok && max_root < PMNET_MIN_MATCHES) ok = false;  // the root also has a None child: not split
+    if (!ok) {
+      if (lane == 0) {
+        acc[kAccNeed] = 0u;
+        atomicAdd((unsigned int*)args.workspace + 8, 1u);
+      }
+      continue;  // stays PMNET_LIG_HEAVY: walked un-split by the last launch
+    }
+    const float best = __int_as_float((int)acc[lane]);
+    const int C = args.n_conf[lig];
+    double s = lane < C ? (double)best : 0.0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    if (lane == 0) {
+      args.out_scores[lig] = (float)(s / (double)C);
+      args.out_status[lig] = PMNET_LIG_OK;
+      if (args.out_stats) {
+        uint32_t* o = args.out_stats + (size_t)lig * 4;
+        o[0] = nodes;
+        o[1] = leaves;
+        o[2] = acc[kAccRows];
+        o[3] = acc[kAccPairs];
+      }
+      acc[kAccNeed] = 0u;
+    }
+    if (args.out_conf) args.out_conf[(size_t)lig * args.conf_stride + lane] = best;
+  }
+}
 
 int sm_count_cached() {
   static int n = 0;
@@ -1188,6 +1488,27 @@ size_t fast_workspace_bytes() {
   return kHeaderBytes + (size_t)sm_count_cached() * fastk::kCtasPerSm * fastk::kWarps * fastk::G_BYTES;
 }
 
+// Node budget of the task-parallel walk for this configuration (0: off). One conformer word only (the task records
+// hold 32 per-conformer scores), and not on a status-restricted re-run.
+uint32_t heavy_budget_of(const PmScoreConfig* in) {
+  if (!in) return kDefaultHeavyBudget;
+  if (in->heavy_budget < 0 || in->rescore_status != 0 || in->max_conformers > 32) return 0u;
+  return in->heavy_budget > 0 ? (uint32_t)in->heavy_budget : kDefaultHeavyBudget;
+}
+
+// bytes of the workspace in front of the heavy-ligand region (header, per-warp scratch, edge table)
+size_t scratch_bytes(int32_t n_model_nodes, int32_t n_model_clusters, const PmScoreConfig* cfg) {
+  PmScoreConfig c;
+  resolve_cfg(cfg, &c, cfg == nullptr || cfg->blocks <= 0);
+  const WarpLayout L = make_layout(n_model_clusters, c.scratch_rows, conf_words(c.max_conformers));
+  // + room for the edge table of a large model (used when the tables do not fit in shared memory)
+  const size_t edge = align_up((size_t)(n_model_nodes > 0 ? n_model_nodes : 0) * (size_t)(n_model_nodes > 0 ? n_model_nodes : 0) * 16, 256);
+  size_t need = kHeaderBytes + (size_t)c.blocks * c.warps_per_block * L.bytes + edge;
+  // the specialised kernel's scratch aliases the general kernel's (they run one after the other on the stream)
+  if (use_fast_kernel(cfg, n_model_nodes, n_model_clusters, -1) && fast_workspace_bytes() > need) need = fast_workspace_bytes();
+  return align_up(need, 256);
+}
+
 }  // namespace
 
 // shared by the other translation units of the library
@@ -1200,15 +1521,9 @@ int pmnet_abi_version(void) { return PMNET_ABI_VERSION; }
 const char* pmnet_last_error_string(void) { return g_err; }
 
 size_t pmnet_score_workspace_bytes(int32_t n_model_nodes, int32_t n_model_clusters, const PmScoreConfig* cfg) {
-  PmScoreConfig c;
-  resolve_cfg(cfg, &c, cfg == nullptr || cfg->blocks <= 0);
-  const WarpLayout L = make_layout(n_model_clusters, c.scratch_rows, conf_words(c.max_conformers));
-  // + room for the edge table of a large model (used when the tables do not fit in shared memory)
-  const size_t edge = align_up((size_t)(n_model_nodes > 0 ? n_model_nodes : 0) * (size_t)(n_model_nodes > 0 ? n_model_nodes : 0) * 16, 256);
-  size_t need = kHeaderBytes + (size_t)c.blocks * c.warps_per_block * L.bytes + edge;
-  // the specialised kernel's scratch aliases the general kernel's (they run one after the other on the stream)
-  if (use_fast_kernel(cfg, n_model_nodes, n_model_clusters, -1) && fast_workspace_bytes() > need) need = fast_workspace_bytes();
-  return need;
+  // the list of heavy ligands and their task records sit behind everything else
+  return scratch_bytes(n_model_nodes, n_model_clusters, cfg) + (heavy_budget_of(cfg) ? kHeavyBytes : 0) +
+         (use_fast_kernel(cfg, n_model_nodes, n_model_clusters, -1) ? kDeferBytes : 0);
 }
 
 int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const float* weights, float* out_scores,
@@ -1277,6 +1592,14 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
   const bool fast = W == 1 && !tg && use_fast_kernel(cfg, model->n_nodes, model->n_clusters, n_cluster_nodes);
   a.only_status = (cfg && cfg->rescore_status != 0) ? cfg->rescore_status : -1;
   a.counter_word = 0;
+  a.heavy_budget = W == 1 ? heavy_budget_of(cfg) : 0u;
+  a.heavy_list = (uint32_t*)((unsigned char*)workspace + scratch_bytes(model->n_nodes, model->n_clusters, cfg));
+  a.heavy_acc = a.heavy_list + kHeavyCap;
+  a.task_rec = a.heavy_acc + (size_t)kHeavyCap * kAccWords;
+  a.task_pass = 0;
+  a.list = nullptr;
+  a.list_count_word = 0;
+  a.list_cap = 0;
   e = cudaMemsetAsync(workspace, 0, kHeaderBytes, stream);
   if (e != cudaSuccess) {
     set_err(cudaGetErrorString(e));
@@ -1293,6 +1616,16 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
     fa.out_stats = out_stats;
     fa.workspace = (unsigned char*)workspace;
     fa.n_cluster_nodes = n_cluster_nodes;
+    fa.heavy_budget = a.heavy_budget;
+    fa.heavy_list = a.heavy_list;
+    fa.heavy_acc = a.heavy_acc;
+    fa.defer_list = nullptr;
+    if (batch->n_ligands <= kDeferCap) {
+      fa.defer_list = (uint32_t*)((unsigned char*)a.heavy_list + (a.heavy_budget ? kHeavyBytes : 0));
+      a.list = fa.defer_list;
+      a.list_count_word = 5;
+      a.list_cap = kDeferCap;
+    }
     const size_t fsmem = fastk::smem_bytes(model->n_nodes, model->n_clusters, n_cluster_nodes);
     e = cudaFuncSetAttribute(fastk::pmnet_score_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
     if (e != cudaSuccess) {
@@ -1334,6 +1667,55 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
   if (e != cudaSuccess) {
     set_err(cudaGetErrorString(e));
     return PMNET_ECUDA;
+  }
+  if (a.heavy_budget != 0u) {
+    // ---- heavy ligands: the task kernel over (ligand, prefix) pairs, the merge of the task records, and the general
+    // kernel once more (no budget) for the heavy ligands the merge had to leave (all three normally find nothing)
+    const void* tfn = tg ? (const void*)pmnet_score_kernel<1, true, true> : (const void*)pmnet_score_kernel<1, false, true>;
+    e = cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_err(cudaGetErrorString(e));
+      return PMNET_ECUDA;
+    }
+    for (int pass = 1; pass <= 2; ++pass) {
+      KernelArgs t = a;
+      t.heavy_budget = 0u;
+      t.only_status = -1;
+      t.counter_word = pass == 1 ? 3 : 6;
+      t.task_pass = pass;
+      void* targs[] = {(void*)&t};
+      e = cudaLaunchKernel(tfn, dim3(c.blocks), dim3(c.warps_per_block * 32), targs, smem, stream);
+      if (e != cudaSuccess) {
+        set_err(cudaGetErrorString(e));
+        return PMNET_ECUDA;
+      }
+      CombineArgs ca;
+      ca.workspace = (unsigned char*)workspace;
+      ca.heavy_list = a.heavy_list;
+      ca.heavy_acc = a.heavy_acc;
+      ca.task_rec = a.task_rec;
+      ca.n_conf = batch->n_conf;
+      ca.out_scores = out_scores;
+      ca.out_conf = out_conf_scores;
+      ca.out_status = out_status;
+      ca.out_stats = out_stats;
+      ca.conf_stride = a.conf_stride;
+      ca.pass = pass;
+      pmnet_heavy_combine_kernel<<<sm_count_cached() * 2, 128, 0, stream>>>(ca);
+    }
+    KernelArgs r = a;
+    r.heavy_budget = 0u;
+    r.only_status = PMNET_LIG_HEAVY;
+    r.counter_word = 4;
+    r.list = a.heavy_list;
+    r.list_count_word = 1;
+    r.list_cap = kHeavyCap;
+    void* rargs[] = {(void*)&r};
+    e = cudaLaunchKernel(fn, dim3(c.blocks), dim3(c.warps_per_block * 32), rargs, smem, stream);
+    if (e != cudaSuccess) {
+      set_err(cudaGetErrorString(e));
+      return PMNET_ECUDA;
+    }
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) {

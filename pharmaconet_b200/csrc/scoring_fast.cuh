@@ -90,6 +90,10 @@ struct FastArgs {
   uint32_t* out_stats;
   unsigned char* workspace;
   int n_cluster_nodes;
+  uint32_t heavy_budget;  // tree nodes after which a ligand is abandoned as PMNET_LIG_HEAVY (0: never)
+  uint32_t* heavy_list;   // ligands abandoned that way (count in header word 1); see scoring.cu
+  uint32_t* heavy_acc;
+  uint32_t* defer_list;   // ligands left PMNET_LIG_DEFERRED, in the order met (count in header word 5); null: no list
 };
 
 __host__ __device__ inline size_t smem_bytes(int nm, int km, int n_cluster_nodes) {
@@ -263,6 +267,7 @@ __global__ void __launch_bounds__(kWarps * 32, PM_FAST_CTAS) pmnet_score_fast_ke
     uint32_t st_nodes = 0, st_leaves = 0, st_rows = 0, st_pairs = 0;
     float best = 0.0f;
     bool defer = (C < 1 || C > 32);
+    bool heavy = false, heavy_denied = false;
 
     if (!defer) {
       const int stride = (C + 3) & ~3;
@@ -601,6 +606,14 @@ __global__ void __launch_bounds__(kWarps * 32, PM_FAST_CTAS) pmnet_score_fast_ke
               const int found = ws.lev_start[y] + src;
               const unsigned alive2 = pm[found];
               ++st_nodes;
+              if (args.heavy_budget != 0u && st_nodes > args.heavy_budget && !heavy_denied) {
+                // abandon: the tree is split into tasks (pmnet_score_batch) - if the list has room
+                if (heavy_append(args.workspace, args.heavy_list, args.heavy_acc, lig, lane)) {
+                  heavy = true;
+                  break;
+                }
+                heavy_denied = true;
+              }
 #if PM_FAST_PREFETCH
               const int myrow = (pf_found == found) ? pf_row : (is_anc ? prow[my_pbase + found] : -1);
               // the next sibling's row indices are requested now (used unless this child is pushed in between)
@@ -737,6 +750,12 @@ __global__ void __launch_bounds__(kWarps * 32, PM_FAST_CTAS) pmnet_score_fast_ke
       score_out = 0.0f;
       best = 0.0f;
       st_nodes = st_leaves = st_rows = 0;
+      // the general kernel's queue: (roughly) longest first like this kernel's own, one ligand per warp at a time
+      if (args.defer_list != nullptr && lane == 0)
+        args.defer_list[atomicAdd((unsigned int*)args.workspace + 5, 1u)] = lig;
+    } else if (heavy) {
+      status = PMNET_LIG_HEAVY;
+      score_out = 0.0f;
     }
     if (lane == 0) {
       args.out_scores[lig] = score_out;

@@ -97,10 +97,12 @@ class ScoreConfig:
     blocks: int = 0
     scratch_rows: int = 0
     rescore_status: int = 0  # != 0: only ligands whose status holds this code are scored (in-place re-runs)
+    heavy_budget: int = 0  # tree nodes after which a ligand's tree is split over many warps (0 default, < 0 never)
 
     def struct(self, max_conformers: int = 32) -> _abi.PmScoreConfig:
         return _abi.PmScoreConfig(
-            self.warps_per_block, self.blocks, self.scratch_rows, int(max_conformers), int(self.rescore_status)
+            self.warps_per_block, self.blocks, self.scratch_rows, int(max_conformers), int(self.rescore_status),
+            int(self.heavy_budget),
         )
 
 

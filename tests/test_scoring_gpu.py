@@ -433,3 +433,66 @@ def test_streamed_screening_mixed_conformer_counts():
     assert np.array_equal(res.scores, whole)
     o = orc.score(c["model"], batch, None)
     assert rel_err(res.scores, o["scores"]).max() <= REL_TOL
+
+
+def _score_with_budget(model, batch, budget, config=None, with_conf=True):
+    """One pmnet_score_batch call with an explicit workspace so that the number of ligands handed to the task-parallel
+    walk (workspace header word 1) can be read back."""
+    from dataclasses import replace
+
+    dm = scoring.DeviceModel(model, "cuda:0")
+    db = scoring.DeviceLigandBatch.from_host(batch, "cuda:0")
+    cfg = replace(config or scoring.ScoreConfig(), heavy_budget=budget)
+    ws = torch.zeros(scoring.workspace_bytes(dm, cfg, db.max_conformers), dtype=torch.uint8, device="cuda:0")
+    out = scoring.score_batch(dm, db, None, cfg, with_stats=True, with_conf=with_conf, workspace=ws)
+    torch.cuda.synchronize()
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    hdr = ws[:64].view(torch.int32).cpu().numpy()
+    res["n_heavy"], res["n_none_tasks"], res["n_unsplit"] = int(hdr[1]), int(hdr[7]), int(hdr[8])
+    return res
+
+
+@pytest.mark.parametrize("name", ["syn0_c32", "syn0_c8", "syn0_c4_deep", "syn0_c5_big", "loose_c8"])
+@pytest.mark.parametrize("general_only", [False, True])
+def test_task_parallel_walk_is_identical_to_single_warp_walk(name, general_only):
+    """PmScoreConfig.heavy_budget: a ligand whose tree outgrows the budget is abandoned and its tree walked by one warp
+    per (level-0 entry, level-1 entry) prefix, then merged. A tiny budget sends a large share of the golden ligands down
+    that path: scores, per-conformer scores, statuses and tree shapes must equal the un-split walk bit for bit (and the
+    oracle's tree shapes)."""
+    c = load_case(name)
+    cfg = scoring.ScoreConfig(16, 148, 8192) if general_only else None
+    base = _score_with_budget(c["model"], c["batch"], -1, cfg)
+    assert base["n_heavy"] == 0
+    split = _score_with_budget(c["model"], c["batch"], 40, cfg)
+    assert split["n_heavy"] > 0
+    assert np.array_equal(split["status"], base["status"]) and not np.any(split["status"] == _abi.LIG_HEAVY)
+    assert np.array_equal(split["scores"], base["scores"])
+    assert np.array_equal(split["conf"], base["conf"])
+    assert np.array_equal(split["stats"], base["stats"])
+    if not general_only:
+        o = orc.score(c["model"], c["batch"], None)
+        ok = split["status"] == _abi.LIG_OK  # (an overflowed ligand has no tree here: score_batch alone does not re-run)
+        assert ok.sum() > 0
+        assert np.array_equal(split["stats"][ok, 0].astype(np.uint32), o["stats"][ok, 0].astype(np.uint32))
+        assert np.array_equal(split["stats"][ok, 1].astype(np.uint32), o["stats"][ok, 1].astype(np.uint32))
+
+
+def test_task_parallel_walk_more_heavy_ligands_than_list_slots():
+    """More ligands over the budget than the list holds (4096): the rest are walked to the end by the warp that has
+    them. With a budget this small the batch also holds level-0 entries whose None child is walked by the second task
+    pass, and ligands that cannot be split at all (fewer than 3 levels, a root that needs a None child): those go to
+    the un-split last pass."""
+    c = load_case("syn0_c32")
+    batch = LigandBatch.from_typed(synthetic.make_ligands(6000, 32, seed=411) + synthetic.make_ligands(500, 5, seed=412, frag_range=(2, 6)))
+    base = _score_with_budget(c["model"], batch, -1)
+    split = _score_with_budget(c["model"], batch, 8)
+    assert split["n_heavy"] > 4096 and split["n_none_tasks"] > 0 and split["n_unsplit"] > 0
+    for k in ("status", "scores", "conf", "stats"):
+        assert np.array_equal(split[k], base[k]), k
+
+
+def test_default_budget_leaves_ordinary_libraries_alone():
+    c = load_case("syn0_c32")
+    out = _score_with_budget(c["model"], c["batch"], 0)
+    assert out["n_heavy"] == 0
+    assert rel_err(out["scores"], c["ref"]).max() <= REL_TOL
