@@ -99,31 +99,37 @@ __host__ __device__ inline WarpLayout make_layout(int n_model_clusters, int scra
 
 constexpr size_t kHeaderBytes = 256;
 // header words: [0] queue of the specialised kernel, [1] number of heavy ligands, [2] queue of the general kernel
-// (deferred pass), [3] queue of the task kernel, [4] queue of the general kernel (last pass: what could not be split),
-// [5] number of deferred ligands, [6] queue of the task kernel's second pass, [7] N(e0) tasks requested for it,
-// [8] heavy ligands left to the un-split last pass (7 and 8: diagnostics, read by the tests)
+// (deferred pass),
+// [5] number of deferred ligands, [9] / [16..] / [24..]: the task rounds (kHdrTask*)
 
 // ---------------------------------------------------------------- heavy ligands (task-parallel DFS)
-// A ligand whose tree exceeds `heavy_budget` nodes is abandoned (status PMNET_LIG_HEAVY) and appended to a list; its
-// tree is then walked by MANY warps: task (e0, e1) = the subtree below the matched level-0 entry e0 and the matched
-// level-1 entry e1, task N(e0) = the subtree below e0's None child. Every task warp recomputes phases 0-1 (cheap next
-// to a tree of 10^5+ nodes), walks its subtree with the prefix forced, leaves a 4-word record and folds its
-// per-conformer best scores into the ligand's accumulator (an integer atomicMax on non-negative floats: exact and
-// order independent). pmnet_heavy_combine_kernel merges the records of a ligand following tree.py:93-102:
-//   pass 1: the (e0, e1) tasks, and N(e0) where e0 has no level-1 candidate (its None child exists for sure). An e0
-//           whose children returned fewer than 4 matches also has a None child: those are requested in a bit mask
-//   pass 2: the requested N(e0) tasks, then the merge of everything
-// A ligand whose ROOT needs a None child (no path with 5 matches - not seen on trees this large) or that cannot be
-// split (fewer than 3 levels, a level 0 / 1 of more than 32 entries) keeps PMNET_LIG_HEAVY and is walked un-split by
-// the last launch. Scores, per-conformer scores and tree statistics are identical to the un-split walk.
-constexpr int kHeavyCap = 4096;           // heavy ligands split per call (more are walked to the end where they are)
-constexpr int kTaskSlots = 32 * 32 + 32;  // (e0, e1) tasks + N(e0) tasks per heavy ligand
-constexpr int kTaskRecWords = 4;          // flags (bit 0 exists, bit 1 cannot split) | K0 << 8 | K1 << 16, ret, nodes, leaves
-constexpr int kAccWords = 40;             // per heavy ligand: best[32], rows, pairs, requested N(e0) mask, -
-constexpr int kAccRows = 32, kAccPairs = 33, kAccNeed = 34;
+// A ligand whose tree exceeds `heavy_budget` nodes is abandoned by its warp (status PMNET_LIG_HEAVY) and appended to a
+// list. The task kernel then walks it with MANY warps, in rounds (one launch each):
+//   round 0   one task per heavy ligand: the whole tree. Whenever a walker has created `heavy_budget` nodes since its
+//             last donation it gives away every not yet visited candidate of the SHALLOWEST node on its path that may
+//             be given away, one task per candidate, into the next round's queue, and goes on with what it keeps
+//   round r   one warp per donated task {heavy slot, depth j, entries chosen at levels 0..j}: it recomputes phases 0-1
+//             (cheap next to 10^4+ tree nodes), replays the path to the donor's node at depth j with every choice
+//             forced (not counted), walks the subtree below the chosen candidate, donating in turn
+//   the last round walks what it gets to the end.
+// A node may give its remaining candidates away only when its None child (tree.py:98: nothing matched, or fewer than 5
+// matches on the best path through it) is already ruled out, and with it the None children of all its ancestors: that
+// holds as soon as a node with >= 5 matches on its path has been created below it (`deep` bit per depth). Then no
+// return value of the donated subtrees is needed by anyone: a task only folds its per-conformer best scores (integer
+// atomicMax on non-negative floats: exact, order independent) and its node / leaf counts (atomicAdd) into the ligand's
+// accumulator, and pmnet_heavy_finish_kernel writes score, status and statistics - identical to the un-split walk.
+constexpr int kHeavyCap = 65536;   // heavy ligands split per call (more are walked to the end where they are)
+constexpr int kAccWords = 40;      // per heavy ligand: best[32], nodes, leaves, rows, pairs, -
+constexpr int kAccNodes = 32, kAccLeaves = 33, kAccRows = 34, kAccPairs = 35;
+constexpr int kTaskWords = 32;     // [0] heavy slot, [1] depth j, [4 + i] entry chosen at level i <= j (~0: the None child)
+constexpr int kTaskCap = 1 << 17;  // tasks per round (a full queue: the walker keeps its candidates)
+constexpr int kTaskRounds = 5;
 constexpr size_t kHeavyBytes =
-    ((size_t)kHeavyCap * 4 * (1 + kAccWords + (size_t)kTaskSlots * kTaskRecWords) + 255) / 256 * 256;
-constexpr uint32_t kDefaultHeavyBudget = 1u << 17;
+    ((size_t)kHeavyCap * 4 * (1 + kAccWords) + 2 * (size_t)kTaskCap * kTaskWords * 4 + 255) / 256 * 256;
+constexpr uint32_t kDefaultHeavyBudget = 1u << 16;
+constexpr int kHdrTaskCount = 16;  // header word 16 + r: tasks queued for round r (r >= 1)
+constexpr int kHdrTaskHead = 24;   // header word 24 + r: queue position of round r
+constexpr int kHdrTaskBad = 9;     // diagnostics: tasks whose replayed path did not match (must stay 0)
 
 // Claim a slot of the heavy list for `lig` (whole warp; false: the list is full) and clear its accumulator.
 __device__ __forceinline__ bool heavy_append(unsigned char* workspace, uint32_t* heavy_list, uint32_t* heavy_acc,
@@ -218,8 +224,8 @@ struct KernelArgs {
   uint32_t heavy_budget;   // tree nodes after which a ligand is abandoned as PMNET_LIG_HEAVY (0: never)
   uint32_t* heavy_list;    // [kHeavyCap] ligand indices (count in header word 1)
   uint32_t* heavy_acc;     // [kHeavyCap][kAccWords]
-  uint32_t* task_rec;      // [kHeavyCap][kTaskSlots][kTaskRecWords]
-  int task_pass;           // task kernel: 1 = (e0, e1) tasks + N(e0) of entries without level-1 candidates, 2 = requested N(e0)
+  uint32_t* task_buf[2];   // [kTaskCap][kTaskWords] each: round r reads buf[r & 1] and fills buf[(r + 1) & 1]
+  int task_round;          // task kernel: 0 .. kTaskRounds - 1
   WarpLayout ly;    // computed once on the host: the kernel reads the offsets from the constant bank
   const float4* edge_g;  // large models: the edge table in the workspace (build_edge_table_kernel)
 };
@@ -358,7 +364,7 @@ __global__ void build_edge_table_kernel(const EdgeTableArgs a) {
 
 #include "scoring_fast.cuh"
 
-// TK = task kernel: the queue runs over (heavy ligand, task slot) pairs and the DFS walks one forced prefix.
+// TK = task kernel: one round of the task-parallel walk of the heavy ligands (see kHeavyCap).
 template <int W, bool TG, bool TK = false>
 __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_kernel(const KernelArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -368,6 +374,11 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
   const int warps_per_block = blockDim.x >> 5;
   const PmModel& gm = args.model;
   const int NM = gm.n_nodes, KM = gm.n_clusters;
+  if (TK) {
+    // nothing queued for this round (the normal case): return before the model is loaded
+    const unsigned int* hdr = (const unsigned int*)args.workspace;
+    if ((args.task_round == 0 ? hdr[1] : hdr[kHdrTaskCount + args.task_round]) == 0u) return;
+  }
 
   // ---- carve shared memory and load the model (once per block)
   SmemModel sm;
@@ -442,35 +453,29 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
   unsigned pend_lig = 0;
   for (;;) {
     unsigned int lig = 0;
-    int task_e0 = 0, task_e1 = -1;  // TK: forced level-0 entry, forced level-1 entry (-1: the None child of e0)
-    uint32_t* task_out = nullptr;
+    int task_j = -1;         // TK: depth of the donor's node whose candidate this task walks (-1: the whole tree)
+    unsigned task_h = 0;     // TK: slot of the ligand in the heavy list
+    unsigned task_word = 0;  // TK: lane l holds word l of the task descriptor
     uint32_t* task_acc = nullptr;
     if (TK) {
       unsigned t = 0;
-      if (lane == 0) t = atomicAdd(counter, 1u);
+      if (lane == 0) t = atomicAdd((unsigned int*)args.workspace + kHdrTaskHead + args.task_round, 1u);
       t = __shfl_sync(kFull, t, 0);
-      unsigned nh = ((const unsigned int*)args.workspace)[1];
-      if (nh > (unsigned)kHeavyCap) nh = kHeavyCap;
-      unsigned h, slot;
-      if (args.task_pass == 1) {
-        if (t >= nh * (unsigned)kTaskSlots) break;
-        h = t / kTaskSlots;
-        slot = t % kTaskSlots;
+      if (args.task_round == 0) {
+        unsigned nh = ((const unsigned int*)args.workspace)[1];
+        if (nh > (unsigned)kHeavyCap) nh = kHeavyCap;
+        if (t >= nh) break;
+        task_h = t;
       } else {
-        if (t >= nh * 32u) break;
-        h = t >> 5;
-        slot = 1024u + (t & 31u);
-        if (!((args.heavy_acc[(size_t)h * kAccWords + kAccNeed] >> (t & 31u)) & 1u)) continue;
+        unsigned nt = ((const unsigned int*)args.workspace)[kHdrTaskCount + args.task_round];
+        if (nt > (unsigned)kTaskCap) nt = kTaskCap;
+        if (t >= nt) break;
+        task_word = args.task_buf[args.task_round & 1][(size_t)t * kTaskWords + lane];
+        task_h = __shfl_sync(kFull, task_word, 0);
+        task_j = (int)__shfl_sync(kFull, task_word, 1);
       }
-      lig = args.heavy_list[h];
-      if (slot < 1024u) {
-        task_e0 = (int)(slot >> 5);
-        task_e1 = (int)(slot & 31u);
-      } else {
-        task_e0 = (int)(slot - 1024u);
-      }
-      task_out = args.task_rec + ((size_t)h * kTaskSlots + slot) * kTaskRecWords;
-      task_acc = args.heavy_acc + (size_t)h * kAccWords;
+      lig = args.heavy_list[task_h];
+      task_acc = args.heavy_acc + (size_t)task_h * kAccWords;
     } else if (args.list != nullptr) {
       bool done = false;
       for (;;) {
@@ -530,16 +535,12 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
     float best[W];
 #pragma unroll
     for (int w = 0; w < W; ++w) best[w] = 0.0f;
-    bool task_skip = false;     // TK: this task does not exist for the ligand (or the ligand cannot be split)
-    bool task_exists = true;    // TK: cleared when the forced prefix turns out not to be part of the tree
-    unsigned task_flags = 0;    // TK: bit 1 = the ligand cannot be split, K0 << 8, K1 << 16
-    int task_ret = 0;           // TK: matches returned to the root (tree.py:100)
+    bool task_bad = false;      // TK: the replayed path did not match the donor's (never: diagnostics only)
     bool heavy = false;         // the tree exceeded the node budget: abandoned, to be split into tasks
     bool heavy_denied = false;  // the list of heavy ligands is full: walk the tree to the end here
 
     if (C < 1 || C > CW) {
       status = PMNET_LIG_UNSUPPORTED;
-      task_flags |= 2u;
     } else {
       const int stride = (C + 3) & ~3;
       const float* xyz = B.coords + (B.coord_off[lig] - B.coord_base);
@@ -632,20 +633,9 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
       if (!overflow && L > 0) {
         if (lane == 0) ws.lev_start[L] = T;
         __syncwarp();
-        if (TK) {
-          const int K0 = ws.lev_start[1] - ws.lev_start[0];
-          const int K1 = L >= 2 ? ws.lev_start[2] - ws.lev_start[1] : 0;
-          task_flags = ((unsigned)K0 << 8) | ((unsigned)K1 << 16);
-          if (L < 3 || K0 > 32 || K1 > 32) {
-            task_flags |= 2u;  // cannot be split by (e0, e1) prefixes
-            task_skip = true;
-          } else if (task_e0 >= K0 || task_e1 >= K1) {
-            task_skip = true;
-          }
-        }
         // node-match records, one lane per entry: count, exclusive scan for the offsets, then fill
         uint32_t rec_used = 0, ml_used = 0;
-        for (int e0 = 0; e0 < T && !overflow && !task_skip; e0 += 32) {
+        for (int e0 = 0; e0 < T && !overflow; e0 += 32) {
           const int e = e0 + lane;
           uint32_t nrec = 0, nml = 0;
           bool toobig = false;
@@ -710,7 +700,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
           ml_used += tml;
         }
         // pair-index base of each entry: V/prow rows of e1 cover all entries of later levels
-        if (!overflow && !task_skip) {
+        if (!overflow) {
           int run = 0;  // running pair count, computed level by level (uniform)
           for (int l = 0; l < L; ++l) {
             const int s = ws.lev_start[l], e_end = ws.lev_start[l + 1];
@@ -727,7 +717,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
           if (run > LY.pair_cap) overflow = true;
         }
         // ligand node-pair distances (LigandEdge.set_distances, ligand.py:349-351), upper triangle of NL x NL
-        if (!overflow && !task_skip) {
+        if (!overflow) {
           for (int i = 0; i < NL - 1; ++i) {
             const int ni = lnode[i];
             float xi[W], yi[W], zi[W];
@@ -756,12 +746,8 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
 
       if (overflow) {
         status = PMNET_LIG_OVERFLOW;
-        task_flags |= 2u;
       } else if (L == 0) {
         status = PMNET_LIG_EMPTY;
-        task_flags |= 2u;
-      } else if (TK && task_skip) {
-        // nothing to walk
       } else {
         // ================= phase 1: self scores and pair table (graph_match.py:222-279)
         // (row / distance indices fit 32 bits: at most 2^17 rows and 255^2 node pairs of 128 conformer slots)
@@ -902,7 +888,6 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
 
         if (overflow) {
           status = PMNET_LIG_OVERFLOW;
-          task_flags |= 2u;
         } else {
 #ifdef PM_TIMING
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm1));
@@ -921,17 +906,28 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
             tot_l[32 * w] = 0.0f;
           }
           if (lane == 0) {
-            st_cursor = TK ? task_e0 : 0;  // lev_start[0] (TK: the forced level-0 entry)
+            st_cursor = 0;  // lev_start[0]
 #pragma unroll
             for (int w = 0; w < W; ++w) st_alive[w] = cfull[w];
           }
           __syncwarp();
-          st_nodes = 1;
+          st_nodes = (TK && task_j >= 0) ? 0u : 1u;  // a task counts what it creates below the replayed path
+          uint32_t deep = 0;   // TK: bit s = a node with >= 5 matches on its path exists below the node at depth s
+          uint32_t mark = 0;   // TK: st_nodes at the last donation
+          uint32_t grain = args.heavy_budget;  // TK: nodes until the next one (a quarter of the budget after the first)
           int d = 0;
           for (;;) {
             // node at depth d; its children live at level y = d
             const int y = d;
             const int phase = __shfl_sync(kFull, st_phase, d);
+            // TK: the nodes at depth <= task_j are the donor's path: one forced child each, then the task is over
+            bool forced = false;
+            int forced_p = 0;
+            if (TK && d <= task_j) {
+              if (phase != 0 || __shfl_sync(kFull, st_nchild, d) != 0) break;
+              forced = true;
+              forced_p = (int)__shfl_sync(kFull, task_word, 4 + d);
+            }
             const int mslot = __shfl_sync(kFull, st_mslot, d);
             const int tslot = __shfl_sync(kFull, st_tslot, d);
             const uint32_t* pm = mk + ws.moff[mslot] * W;
@@ -1003,6 +999,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
               st_nodes += nleaf;
               st_leaves += nleaf;
               const int nmatch = __shfl_sync(kFull, st_nmatch, d);
+              if (TK && nleaf > 0 && nmatch + 1 >= PMNET_MIN_MATCHES) deep |= (2u << d) - 1u;
               if (lane == d) st_maxm = nleaf > 0 ? 1 : 0;
               if (nleaf == 0 || nmatch + 1 < PMNET_MIN_MATCHES) {
                 // the None leaf (tree.py:98)
@@ -1018,7 +1015,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
             } else if (phase == 0) {
               int cur = __shfl_sync(kFull, st_cursor, d);
               const int end = ws.lev_start[y + 1];
-              const bool first_visit = cur < end;
+              if (forced) cur = forced_p < 0 ? end : forced_p;
               int found = -1;
               unsigned alive2[W];
 #pragma unroll
@@ -1042,16 +1039,15 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
                 }
                 cur += 32;
               }
-              if (TK && first_visit && ((d == 1 && task_e1 >= 0 && found != ws.lev_start[1] + task_e1) ||
-                                        (d == 0 && found != task_e0))) {
-                task_exists = false;  // the forced entry is not a candidate below its parent
+              if (forced && forced_p >= 0 && found != forced_p) {
+                task_bad = true;  // cannot happen: the path is recomputed from the same inputs
                 break;
               }
               if (found >= 0) {
                 // ---- matched child (y, found): ClusterMatchTree.__init__ (tree.py:33-41); it is not a leaf
-                ++st_nodes;
+                if (!(TK && d < task_j)) ++st_nodes;
                 if (!TK && args.heavy_budget != 0u && st_nodes > args.heavy_budget && !heavy_denied) {
-                  // abandon: the tree is split into tasks (pmnet_score_batch) - if the list has room
+                  // abandon: the tree is walked by the task kernel (pmnet_score_batch) - if the list has room
                   if (heavy_append(args.workspace, args.heavy_list, args.heavy_acc, lig, lane)) {
                     heavy = true;
                     break;
@@ -1059,8 +1055,63 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
                   heavy_denied = true;
                 }
                 if (lane == d) {
-                  st_cursor = (TK && d <= 1) ? end : found + 1;  // TK: the prefix nodes have exactly one child
+                  st_cursor = forced ? end : found + 1;
                   st_nchild += 1;
+                }
+                if (TK && __shfl_sync(kFull, st_nmatch, d) + 1 >= PMNET_MIN_MATCHES) deep |= (2u << d) - 1u;
+                if (TK && args.heavy_budget != 0u && d > task_j && st_nodes - mark > grain) {
+                  // ---- donate the unvisited candidates of the shallowest node that may give them away
+                  mark = st_nodes;
+                  const int pe = __shfl_sync(kFull, st_entry, (lane - 3) & 31);  // lane 4 + i: the entry chosen at level i
+                  unsigned int* const qcount = (unsigned int*)args.workspace + kHdrTaskCount + args.task_round + 1;
+                  uint32_t* const qout = args.task_buf[(args.task_round + 1) & 1];
+                  for (int s = task_j + 1; s <= d; ++s) {
+                    if (!((deep >> s) & 1u)) continue;
+                    const int cs = __shfl_sync(kFull, st_cursor, s), es = ws.lev_start[s + 1];
+                    const uint32_t* pms = mk + ws.moff[__shfl_sync(kFull, st_mslot, s)] * W;
+                    int cnt = 0;
+                    for (int b = cs; b < es; b += 32) {
+                      unsigned anyw = 0;
+                      if (b + lane < es)
+#pragma unroll
+                        for (int w = 0; w < W; ++w) anyw |= pms[(b + lane) * W + w];
+                      cnt += __popc(__ballot_sync(kFull, anyw != 0u));
+                    }
+                    if (cnt == 0) continue;
+                    unsigned base = 0xffffffffu;  // reserve cnt queue slots (all or nothing)
+                    if (lane == 0) {
+                      unsigned old = *(volatile unsigned int*)qcount;
+                      while (old + (unsigned)cnt <= (unsigned)kTaskCap) {
+                        const unsigned prev = atomicCAS(qcount, old, old + (unsigned)cnt);
+                        if (prev == old) {
+                          base = old;
+                          break;
+                        }
+                        old = prev;
+                      }
+                    }
+                    base = __shfl_sync(kFull, base, 0);
+                    if (base == 0xffffffffu) break;  // the queue is full: keep everything
+                    for (int b = cs; b < es; b += 32) {
+                      unsigned anyw = 0;
+                      if (b + lane < es)
+#pragma unroll
+                        for (int w = 0; w < W; ++w) anyw |= pms[(b + lane) * W + w];
+                      for (unsigned bal = __ballot_sync(kFull, anyw != 0u); bal; bal &= bal - 1) {
+                        const int c = b + __ffs(bal) - 1;
+                        uint32_t wv = 0;
+                        if (lane == 0) wv = task_h;
+                        else if (lane == 1) wv = (uint32_t)s;
+                        else if (lane >= 4 && lane - 4 < s) wv = (uint32_t)pe;
+                        else if (lane - 4 == s) wv = (uint32_t)c;
+                        qout[(size_t)base * kTaskWords + lane] = wv;
+                        ++base;
+                      }
+                    }
+                    if (lane == s) st_cursor = es;
+                    grain = args.heavy_budget >> 2;
+                    break;  // one node per donation
+                  }
                 }
                 // everything that depends only on `found` is requested first: the ancestors' pair-row indices,
                 // the self row index, the parent's totals and the first chunk of the child's masks
@@ -1107,10 +1158,6 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
 #pragma unroll
                   for (int w = 0; w < W; ++w) any0 |= pmv[w] & alive2[w] & vtv[w];
                   if (T - end <= 32 && !__any_sync(kFull, any0 != 0u)) {
-                    if (TK && d == 0 && task_e1 >= 0) {
-                      task_exists = false;  // e0 has no candidate below it: only its N(e0) task exists
-                      break;
-                    }
                     st_nodes += L - d - 1;
                     ++st_leaves;
 #pragma unroll
@@ -1180,6 +1227,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
                   }
                   st_nodes += nleaf;
                   st_leaves += nleaf;
+                  if (TK && nmatch + 1 >= PMNET_MIN_MATCHES) deep |= (2u << d) - 1u;  // (nleaf > 0 here)
                   if (nmatch + 1 < PMNET_MIN_MATCHES) {
                     // the child's None leaf (tree.py:98: too few matches on the path)
                     ++st_nodes;
@@ -1190,23 +1238,6 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
                   }
                   if (lane == d) st_maxm = max(st_maxm, 2);  // the child returns 1 (a matched leaf) + 1 (itself)
                   continue;
-                }
-                int child_cursor = end;
-                if (TK && d == 0) {
-                  // does e0 have a level-1 candidate at all? (level 1 has at most 32 entries: all in this chunk)
-                  unsigned anyl1 = 0;
-#pragma unroll
-                  for (int w = 0; w < W; ++w) anyl1 |= pmv[w] & alive2[w] & vtv[w];
-                  const bool has_l1 = __any_sync(kFull, anyl1 != 0u && e2a < ws.lev_start[2]);
-                  if (task_e1 < 0) {
-                    if (has_l1 && args.task_pass == 1) {
-                      task_exists = false;  // pass 1 walks N(e0) only when e0 has no level-1 candidate
-                      break;
-                    }
-                    child_cursor = ws.lev_start[2];  // nothing to find: the None child follows (tree.py:98)
-                  } else {
-                    child_cursor = end + task_e1;
-                  }
                 }
                 // the child's candidate masks: parent mask & conformers alive in the child & pair validity.
                 // (depth d + 1's slot was last read by other lanes while the previous child's subtree was walked)
@@ -1222,8 +1253,9 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
                 }
 #pragma unroll
                 for (int w = 0; w < W; ++w) tot_l[(d + 1) * CW + 32 * w] = t[w] + acc[w];
+                if (TK) deep = (deep & ((2u << d) - 1u)) | (nmatch >= PMNET_MIN_MATCHES ? (2u << d) : 0u);
                 if (lane == d + 1) {
-                  st_cursor = child_cursor;
+                  st_cursor = end;
                   st_maxm = 0;
                   st_nchild = 0;
                   st_phase = 0;
@@ -1243,12 +1275,11 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
               const int nchild = __shfl_sync(kFull, st_nchild, d);
               const int nmatch = __shfl_sync(kFull, st_nmatch, d);
               const int maxm = __shfl_sync(kFull, st_maxm, d);
-              // TK: the None children of the prefix nodes (the root, and e0 in an (e0, e1) task) are not this task's
-              // business - the combine step checks that the tree does not have them
-              const bool prefix_node = TK && (d == 0 || (d == 1 && task_e1 >= 0));
-              if (!prefix_node && (nchild == 0 || nmatch + maxm < PMNET_MIN_MATCHES)) {
+              // (TK, replayed path: the None child is walked iff the donor's path goes through it)
+              if (forced ? forced_p < 0 : (nchild == 0 || nmatch + maxm < PMNET_MIN_MATCHES)) {
                 // the None child is not a leaf here (y < L - 1): same masks and totals, one level down
-                ++st_nodes;
+                if (!forced) ++st_nodes;
+                if (TK) deep = (deep & ((2u << d) - 1u)) | (nmatch >= PMNET_MIN_MATCHES ? (2u << d) : 0u);
                 if (lane == d) st_phase = 1;
                 unsigned alive[W];
 #pragma unroll
@@ -1280,7 +1311,6 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
               d = d - 1;
             }
           }
-          if (TK) task_ret = __shfl_sync(kFull, st_maxm, 0);
           // mean over conformers (graph_match.py:109)
           double s = 0.0;
 #pragma unroll
@@ -1292,17 +1322,19 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
       (void)lane_on;
     }
     if (TK) {
-      // the task's record (pmnet_heavy_combine_kernel); W == 1
-      const bool ex = task_exists && !task_skip && status == PMNET_LIG_OK && !(task_flags & 2u);
-      if (lane == 0) {
-        *(uint4*)task_out = make_uint4(task_flags | (ex ? 1u : 0u), (uint32_t)task_ret, st_nodes, st_leaves);
-        if (ex) {
+      // fold the task into the ligand's accumulator (pmnet_heavy_finish_kernel); W == 1
+      if (status != PMNET_LIG_OK || task_bad) {
+        if (lane == 0) atomicAdd((unsigned int*)args.workspace + kHdrTaskBad, 1u);
+      } else {
+        // scores are >= 0 (best starts at 0): their bit patterns order like integers
+        atomicMax((int*)task_acc + lane, __float_as_int(best[0]));
+        if (lane == 0) {
+          atomicAdd(task_acc + kAccNodes, st_nodes);
+          atomicAdd(task_acc + kAccLeaves, st_leaves);
           task_acc[kAccRows] = st_rows;  // the same in every task of the ligand
           task_acc[kAccPairs] = st_pairs;
         }
       }
-      // scores are >= 0 (best starts at 0): their bit patterns order like integers
-      if (ex) atomicMax((int*)task_acc + lane, __float_as_int(best[0]));
       __syncwarp();
       continue;
     }
@@ -1337,24 +1369,20 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
 }
 
 
-// One warp per heavy ligand: merge the task records into the ligand's score, statistics and status (see the notes
-// at kHeavyCap). pass 1 finishes the ligands that need no further N(e0) task and requests those tasks for the others;
-// pass 2 finishes the others.
-struct CombineArgs {
-  unsigned char* workspace;
+// One warp per heavy ligand, after the last task round: score, status and statistics from the accumulator.
+struct FinishArgs {
+  const unsigned char* workspace;
   const uint32_t* heavy_list;
-  uint32_t* heavy_acc;
-  const uint32_t* task_rec;
+  const uint32_t* heavy_acc;
   const int32_t* n_conf;
   float* out_scores;
   float* out_conf;
   int32_t* out_status;
   uint32_t* out_stats;
   int conf_stride;
-  int pass;
 };
 
-__global__ void __launch_bounds__(128) pmnet_heavy_combine_kernel(const CombineArgs args) {
+__global__ void __launch_bounds__(128) pmnet_heavy_finish_kernel(const FinishArgs args) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1362,82 +1390,21 @@ __global__ void __launch_bounds__(128) pmnet_heavy_combine_kernel(const CombineA
   if (nh > (unsigned)kHeavyCap) nh = kHeavyCap;
   for (unsigned h = warp; h < nh; h += nwarps) {
     const uint32_t lig = args.heavy_list[h];
-    uint32_t* const acc = args.heavy_acc + (size_t)h * kAccWords;
-    const uint4* const rec = (const uint4*)(args.task_rec + (size_t)h * kTaskSlots * kTaskRecWords);
-    const uint32_t requested = acc[kAccNeed];
-    if (args.pass == 2 && requested == 0u) continue;  // finished (or given up) in pass 1
-    const uint32_t f0 = rec[0].x;
-    bool ok = (f0 & 2u) == 0u;
-    const int K0 = (int)((f0 >> 8) & 255u), K1 = (int)((f0 >> 16) & 255u);
-    if (K0 < 1 || K0 > 32 || K1 < 1 || K1 > 32) ok = false;
-    uint32_t nodes = 1, leaves = 0, need = 0;
-    int max_root = 0;
-    for (int e0 = 0; e0 < K0 && ok; ++e0) {
-      const uint4 r = rec[e0 * 32 + lane];
-      const bool ex = lane < K1 && (r.x & 1u);
-      const unsigned bal = __ballot_sync(kFull, ex);
-      const uint4 rn = rec[1024 + e0];
-      const bool exn = (rn.x & 1u) != 0u;
-      const bool want_n = bal == 0u || ((requested >> e0) & 1u);  // N(e0) is part of the tree
-      if (exn != want_n) {
-        ok = false;  // not a tree this split describes
-        break;
-      }
-      int m = 0;  // most matches below e0
-      nodes += 1u;
-      if (bal) {
-        m = ex ? (int)r.y - 1 : 0;
-        uint32_t nn = ex ? r.z - 2u : 0u, nl = ex ? r.w : 0u;
-        for (int o = 16; o > 0; o >>= 1) {
-          m = max(m, __shfl_xor_sync(kFull, m, o));
-          nn += __shfl_xor_sync(kFull, nn, o);
-          nl += __shfl_xor_sync(kFull, nl, o);
-        }
-        nodes += nn;
-        leaves += nl;
-        // tree.py:98 at e0 (one match on the path): its children returned too few matches - a None child follows
-        if (1 + m < PMNET_MIN_MATCHES && !exn) need |= 1u << e0;
-      }
-      if (exn) {
-        m = max(m, (int)rn.y - 1);
-        nodes += rn.z - 2u;
-        leaves += rn.w;
-      }
-      max_root = max(max_root, 1 + m);
-    }
-    if (ok && need != 0u) {
-      if (args.pass == 1) {
-        if (lane == 0) {
-          acc[kAccNeed] = need;  // pass 2 walks these and comes back
-          atomicAdd((unsigned int*)args.workspace + 7, (unsigned)__popc(need));
-        }
-        continue;
-      }
-      ok = false;  // (cannot happen: pass 2 has walked every requested N(e0))
-    }
-    if (ok && max_root < PMNET_MIN_MATCHES) ok = false;  // the root also has a None child: not split
-    if (!ok) {
-      if (lane == 0) {
-        acc[kAccNeed] = 0u;
-        atomicAdd((unsigned int*)args.workspace + 8, 1u);
-      }
-      continue;  // stays PMNET_LIG_HEAVY: walked un-split by the last launch
-    }
+    const uint32_t* const acc = args.heavy_acc + (size_t)h * kAccWords;
     const float best = __int_as_float((int)acc[lane]);
     const int C = args.n_conf[lig];
-    double s = lane < C ? (double)best : 0.0;
+    double s = lane < C ? (double)best : 0.0;  // mean over conformers (graph_match.py:109), like the walkers
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
     if (lane == 0) {
       args.out_scores[lig] = (float)(s / (double)C);
       args.out_status[lig] = PMNET_LIG_OK;
       if (args.out_stats) {
         uint32_t* o = args.out_stats + (size_t)lig * 4;
-        o[0] = nodes;
-        o[1] = leaves;
+        o[0] = acc[kAccNodes];
+        o[1] = acc[kAccLeaves];
         o[2] = acc[kAccRows];
         o[3] = acc[kAccPairs];
       }
-      acc[kAccNeed] = 0u;
     }
     if (args.out_conf) args.out_conf[(size_t)lig * args.conf_stride + lane] = best;
   }
@@ -1595,8 +1562,9 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
   a.heavy_budget = W == 1 ? heavy_budget_of(cfg) : 0u;
   a.heavy_list = (uint32_t*)((unsigned char*)workspace + scratch_bytes(model->n_nodes, model->n_clusters, cfg));
   a.heavy_acc = a.heavy_list + kHeavyCap;
-  a.task_rec = a.heavy_acc + (size_t)kHeavyCap * kAccWords;
-  a.task_pass = 0;
+  a.task_buf[0] = a.heavy_acc + (size_t)kHeavyCap * kAccWords;
+  a.task_buf[1] = a.task_buf[0] + (size_t)kTaskCap * kTaskWords;
+  a.task_round = 0;
   a.list = nullptr;
   a.list_count_word = 0;
   a.list_cap = 0;
@@ -1669,53 +1637,38 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
     return PMNET_ECUDA;
   }
   if (a.heavy_budget != 0u) {
-    // ---- heavy ligands: the task kernel over (ligand, prefix) pairs, the merge of the task records, and the general
-    // kernel once more (no budget) for the heavy ligands the merge had to leave (all three normally find nothing)
+    // ---- heavy ligands: the rounds of the task kernel (each returns at once when its queue is empty), then the
+    // kernel that turns the accumulators into scores
     const void* tfn = tg ? (const void*)pmnet_score_kernel<1, true, true> : (const void*)pmnet_score_kernel<1, false, true>;
     e = cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_err(cudaGetErrorString(e));
       return PMNET_ECUDA;
     }
-    for (int pass = 1; pass <= 2; ++pass) {
+    for (int round = 0; round < kTaskRounds; ++round) {
       KernelArgs t = a;
-      t.heavy_budget = 0u;
+      t.heavy_budget = round == kTaskRounds - 1 ? 0u : a.heavy_budget;  // the last round walks everything to the end
       t.only_status = -1;
-      t.counter_word = pass == 1 ? 3 : 6;
-      t.task_pass = pass;
+      t.list = nullptr;
+      t.task_round = round;
       void* targs[] = {(void*)&t};
       e = cudaLaunchKernel(tfn, dim3(c.blocks), dim3(c.warps_per_block * 32), targs, smem, stream);
       if (e != cudaSuccess) {
         set_err(cudaGetErrorString(e));
         return PMNET_ECUDA;
       }
-      CombineArgs ca;
-      ca.workspace = (unsigned char*)workspace;
-      ca.heavy_list = a.heavy_list;
-      ca.heavy_acc = a.heavy_acc;
-      ca.task_rec = a.task_rec;
-      ca.n_conf = batch->n_conf;
-      ca.out_scores = out_scores;
-      ca.out_conf = out_conf_scores;
-      ca.out_status = out_status;
-      ca.out_stats = out_stats;
-      ca.conf_stride = a.conf_stride;
-      ca.pass = pass;
-      pmnet_heavy_combine_kernel<<<sm_count_cached() * 2, 128, 0, stream>>>(ca);
     }
-    KernelArgs r = a;
-    r.heavy_budget = 0u;
-    r.only_status = PMNET_LIG_HEAVY;
-    r.counter_word = 4;
-    r.list = a.heavy_list;
-    r.list_count_word = 1;
-    r.list_cap = kHeavyCap;
-    void* rargs[] = {(void*)&r};
-    e = cudaLaunchKernel(fn, dim3(c.blocks), dim3(c.warps_per_block * 32), rargs, smem, stream);
-    if (e != cudaSuccess) {
-      set_err(cudaGetErrorString(e));
-      return PMNET_ECUDA;
-    }
+    FinishArgs fa;
+    fa.workspace = (const unsigned char*)workspace;
+    fa.heavy_list = a.heavy_list;
+    fa.heavy_acc = a.heavy_acc;
+    fa.n_conf = batch->n_conf;
+    fa.out_scores = out_scores;
+    fa.out_conf = out_conf_scores;
+    fa.out_status = out_status;
+    fa.out_stats = out_stats;
+    fa.conf_stride = a.conf_stride;
+    pmnet_heavy_finish_kernel<<<sm_count_cached() * 2, 128, 0, stream>>>(fa);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -106,6 +106,19 @@ class ScoreConfig:
         )
 
 
+def launches_per_call(config: "ScoreConfig | None" = None, max_conformers: int = 32) -> int:
+    """Kernels one pmnet_score_batch call enqueues (csrc/scoring.cu): the specialised kernel (default launch shape and
+    <= 32 conformers only; models whose tables do not fit in shared memory skip it), the general kernel, and - unless
+    heavy_budget < 0, more than 32 conformers or a status-restricted re-run - the five rounds of the task kernel (each
+    returns at once when nothing was queued for it) plus the kernel that finishes the heavy ligands."""
+    cfg = config or ScoreConfig()
+    custom = cfg.warps_per_block > 0 or cfg.blocks > 0 or cfg.scratch_rows > 0 or cfg.rescore_status != 0
+    n = 1 + int(not custom and max_conformers <= 32)
+    if cfg.heavy_budget >= 0 and cfg.rescore_status == 0 and max_conformers <= 32:
+        n += 6
+    return n
+
+
 def conf_stride(max_conformers: int) -> int:
     """Row length of the per-conformer output: 32 conformers per lane word, 1 / 2 / 4 words."""
     return 32 if max_conformers <= 32 else (64 if max_conformers <= 64 else 128)

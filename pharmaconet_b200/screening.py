@@ -22,8 +22,8 @@ import torch
 from . import _abi
 from .packing import LigandBatch, PackedModel
 from .scoring import (
-    DeviceLigandBatch, DeviceModel, ScoreConfig, cost_order, order_workspace_bytes as _lib_order_bytes, rescore_overflowed,
-    rescore_overflowed_device, score_batch, topk, warn_unscored, workspace_bytes,
+    DeviceLigandBatch, DeviceModel, ScoreConfig, cost_order, launches_per_call, order_workspace_bytes as _lib_order_bytes,
+    rescore_overflowed, rescore_overflowed_device, score_batch, topk, warn_unscored, workspace_bytes,
 )  # fmt: skip
 
 
@@ -156,7 +156,8 @@ class Screener:
 
     # ------------------------------------------------------------------ device-resident shard: one launch
     def screen_device(self, batch: DeviceLigandBatch, id_base: int = 0, gather: bool = True) -> ScreenResult:
-        launches = 4  # two scoring kernels (specialised + general) + id fill + top-k write-out (the sort passes are CUB's)
+        # the scoring kernels + id fill + top-k write-out (the sort passes are CUB's)
+        launches = launches_per_call(self.config, batch.max_conformers) + 2
         if self.lpt and batch.order is None:
             # once per resident library and model: the order only depends on topologies and the model's cluster types
             batch.set_order(cost_order(self.model, batch))
@@ -270,7 +271,7 @@ class Screener:
             )  # fmt: skip
             slot.free.record(slot.stream)
             spans.append((pos, nb, a))
-            launches += 2 + int(self.lpt)
+            launches += launches_per_call(scfg, max(1, lib.max_conformers)) + int(self.lpt)
             pos += nb
         for slot in (self._slots or [])[: len(blocks)]:
             main.wait_event(slot.free)
@@ -362,7 +363,7 @@ def screen_models(
     for dm, (o, ks, ki) in zip(dms, outs):
         # (first host sync of the call) overflowed ligands are re-run in place on the resident shard
         n_over = rescore_overflowed_device(dm, batch, o, weights)
-        launches = 4
+        launches = launches_per_call(None, batch.max_conformers) + 2
         if n_over:
             warn_unscored(o["status"], "screen_models")
             ks, ki = topk(o["scores"], k, id_base)

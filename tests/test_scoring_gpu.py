@@ -259,7 +259,9 @@ def test_streamed_screening_ramp_up_spans():
     assert np.array_equal(res.scores, whole)
     order = np.lexsort((np.arange(9000), -whole.astype(np.float64)))[:64]
     assert np.array_equal(res.topk_ids.cpu().numpy(), order)
-    assert res.launches == 5 * 5  # four ramp spans + the second block, each: cost kernel, 2 scoring kernels, id fill, top-k
+    # four ramp spans + the second block, each: cost kernel, the scoring call's kernels (specialised, general, five task
+    # rounds, heavy-ligand finish), id fill, top-k
+    assert res.launches == 5 * (1 + scoring.launches_per_call() + 2) == 5 * 11
 
 
 def test_cost_order_is_a_stable_permutation_and_does_not_change_scores():
@@ -447,24 +449,25 @@ def _score_with_budget(model, batch, budget, config=None, with_conf=True):
     out = scoring.score_batch(dm, db, None, cfg, with_stats=True, with_conf=with_conf, workspace=ws)
     torch.cuda.synchronize()
     res = {k: v.cpu().numpy() for k, v in out.items()}
-    hdr = ws[:64].view(torch.int32).cpu().numpy()
-    res["n_heavy"], res["n_none_tasks"], res["n_unsplit"] = int(hdr[1]), int(hdr[7]), int(hdr[8])
+    hdr = ws[:256].view(torch.int32).cpu().numpy()
+    # header words: [1] ligands over the budget, [16 + r] tasks donated to round r, [9] replay mismatches (never)
+    res["n_heavy"], res["n_tasks"], res["n_bad"] = int(hdr[1]), [int(x) for x in hdr[17:21]], int(hdr[9])
     return res
 
 
 @pytest.mark.parametrize("name", ["syn0_c32", "syn0_c8", "syn0_c4_deep", "syn0_c5_big", "loose_c8"])
 @pytest.mark.parametrize("general_only", [False, True])
 def test_task_parallel_walk_is_identical_to_single_warp_walk(name, general_only):
-    """PmScoreConfig.heavy_budget: a ligand whose tree outgrows the budget is abandoned and its tree walked by one warp
-    per (level-0 entry, level-1 entry) prefix, then merged. A tiny budget sends a large share of the golden ligands down
-    that path: scores, per-conformer scores, statuses and tree shapes must equal the un-split walk bit for bit (and the
-    oracle's tree shapes)."""
+    """PmScoreConfig.heavy_budget: a ligand whose tree outgrows the budget is abandoned and walked by the task kernel,
+    whose walkers give unvisited candidates away as tasks every `budget` nodes. A tiny budget sends a large share of
+    the golden ligands down that path and splits them many times: scores, per-conformer scores, statuses and tree
+    shapes must equal the un-split walk bit for bit (and the oracle's tree shapes)."""
     c = load_case(name)
     cfg = scoring.ScoreConfig(16, 148, 8192) if general_only else None
     base = _score_with_budget(c["model"], c["batch"], -1, cfg)
     assert base["n_heavy"] == 0
     split = _score_with_budget(c["model"], c["batch"], 40, cfg)
-    assert split["n_heavy"] > 0
+    assert split["n_heavy"] > 0 and split["n_tasks"][0] > 0 and split["n_bad"] == 0
     assert np.array_equal(split["status"], base["status"]) and not np.any(split["status"] == _abi.LIG_HEAVY)
     assert np.array_equal(split["scores"], base["scores"])
     assert np.array_equal(split["conf"], base["conf"])
@@ -477,17 +480,30 @@ def test_task_parallel_walk_is_identical_to_single_warp_walk(name, general_only)
         assert np.array_equal(split["stats"][ok, 1].astype(np.uint32), o["stats"][ok, 1].astype(np.uint32))
 
 
-def test_task_parallel_walk_more_heavy_ligands_than_list_slots():
-    """More ligands over the budget than the list holds (4096): the rest are walked to the end by the warp that has
-    them. With a budget this small the batch also holds level-0 entries whose None child is walked by the second task
-    pass, and ligands that cannot be split at all (fewer than 3 levels, a root that needs a None child): those go to
-    the un-split last pass."""
+def test_task_parallel_walk_full_queues():
+    """A budget of 8 nodes on 6500 ligands: nearly every ligand goes to the task kernel, tasks are donated in every
+    round (paths through None children included), the queues of the later rounds (131 072 tasks) fill up - a walker
+    that cannot donate keeps its candidates - and the last round finishes what is left."""
     c = load_case("syn0_c32")
     batch = LigandBatch.from_typed(synthetic.make_ligands(6000, 32, seed=411) + synthetic.make_ligands(500, 5, seed=412, frag_range=(2, 6)))
     base = _score_with_budget(c["model"], batch, -1)
     split = _score_with_budget(c["model"], batch, 8)
-    assert split["n_heavy"] > 4096 and split["n_none_tasks"] > 0 and split["n_unsplit"] > 0
+    assert split["n_heavy"] > 4096 and min(split["n_tasks"]) > 0 and split["n_bad"] == 0
+    assert max(split["n_tasks"]) > 100000
     for k in ("status", "scores", "conf", "stats"):
+        assert np.array_equal(split[k], base[k]), k
+
+
+def test_task_parallel_walk_full_heavy_list():
+    """More ligands over the budget than the list of heavy ligands holds (65 536): the rest are walked to the end by
+    the warp that has them."""
+    c = load_case("syn0_c8")
+    base_lib = LigandBatch.from_typed(synthetic.make_ligands(3000, 8, seed=421))
+    batch = base_lib.select(np.tile(np.arange(3000), 30))
+    base = _score_with_budget(c["model"], batch, -1, with_conf=False)
+    split = _score_with_budget(c["model"], batch, 8, with_conf=False)
+    assert split["n_heavy"] > 65536 and split["n_bad"] == 0
+    for k in ("status", "scores", "stats"):
         assert np.array_equal(split[k], base[k]), k
 
 

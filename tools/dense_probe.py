@@ -58,23 +58,8 @@ for b in [int(x) for x in a.budgets.split(",")]:
         for i in np.argsort(-(t01 + t2))[:8]:
             print(f"    ligand {i}: phases 0-1 {t01[i]:.0f} us, DFS {t2[i]:.0f} us, nodes {nodes[i]:.0f}, leaves {stats[i, 1]:.0f}")
     if a.profile and nh > 0:
-        HEAVY_CAP, SLOTS, WORDS, ACC = 4096, 1056, 4, 40
-        hbytes = (HEAVY_CAP * 4 * (1 + ACC + SLOTS * WORDS) + 255) // 256 * 256
-        off = ws.numel() - hbytes - (0 if a.general else (1 << 20) * 4)
-        r0 = off + HEAVY_CAP * 4 * (1 + ACC)
-        rec = ws[r0: r0 + HEAVY_CAP * SLOTS * WORDS * 4].view(torch.int32).view(HEAVY_CAP, SLOTS, WORDS)
-        hdr = ws[:64].view(torch.int32).cpu().numpy()
-        print(f"  N(e0) tasks of the second pass {hdr[7]}, ligands left un-split {hdr[8]}, deferred {hdr[5]}")
-        rec = rec[: min(nh, HEAVY_CAP)].cpu().numpy().view(np.uint32)
-        ex = (rec[:, :, 0] & 1) == 1
-        tn = np.where(ex, rec[:, :, 2], 0).astype(np.float64)
-        tot = tn.sum(1)
-        big = np.argsort(-tot)[:5]
-        print(f"  tasks per heavy ligand: mean {ex.sum(1).mean():.1f}; largest task / ligand total: mean {np.mean(tn.max(1) / tot):.2f}; "
-              f"largest task overall {tn.max():.0f} nodes; all tasks {tn.sum():.3e} nodes")
-        for h in big:
-            t = np.sort(tn[h][ex[h]])[::-1]
-            print(f"    ligand total {tot[h]:.0f} in {ex[h].sum()} tasks: top {t[:6].astype(int).tolist()}")
+        hdr = ws[:256].view(torch.int32).cpu().numpy()
+        print(f"  tasks donated to rounds 1..4: {hdr[17:21].tolist()}, replay mismatches {hdr[9]}, deferred {hdr[5]}")
         from torch.profiler import ProfilerActivity, profile
 
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
