@@ -34,6 +34,10 @@ namespace fastk {
 #ifndef PM_FAST_PREFETCH
 #define PM_FAST_PREFETCH 0  // measured: 71.4 vs 70.0 M conformers/s without / with the sibling prefetch
 #endif
+#ifndef PM_FAST_HEAVY_CHECK
+#define PM_FAST_HEAVY_CHECK 3  // where the node budget is tested: 0 child created, 1 child pushed, 2 never, 3 node popped (measured:
+                               // 69.1 / 70.2 / 71.6 / 72.3 M conformers/s), 4 node popped at depth <= 3
+#endif
 #ifndef PM_FAST_CTAS
 #define PM_FAST_CTAS 1      // CTAs per SM (PM_FAST_WARPS warps each)
 #endif
@@ -251,6 +255,7 @@ __global__ void __launch_bounds__(kWarps * 32, PM_FAST_CTAS) pmnet_score_fast_ke
   int32_t* const prow = (int32_t*)(wbase + G_PROW);
   unsigned int* const counter = (unsigned int*)args.workspace;
   const PmLigandBatch& B = args.batch;
+  const uint32_t budget = args.heavy_budget != 0u ? args.heavy_budget : 0xffffffffu;
 
   for (;;) {
     unsigned int lig = 0;
@@ -267,7 +272,8 @@ __global__ void __launch_bounds__(kWarps * 32, PM_FAST_CTAS) pmnet_score_fast_ke
     uint32_t st_nodes = 0, st_leaves = 0, st_rows = 0, st_pairs = 0;
     float best = 0.0f;
     bool defer = (C < 1 || C > 32);
-    bool heavy = false, heavy_denied = false;
+    bool heavy = false;
+    uint32_t node_limit = budget;  // nodes after which the ligand is handed to the task rounds (~0: never)
 
     if (!defer) {
       const int stride = (C + 3) & ~3;
@@ -577,6 +583,9 @@ __global__ void __launch_bounds__(kWarps * 32, PM_FAST_CTAS) pmnet_score_fast_ke
 #endif
           unsigned cand = (ws.lev_start[1] >= 32) ? kFull : ((1u << ws.lev_start[1]) - 1u);  // every entry of level 0
           bool hadc = true;
+#if PM_FAST_HEAVY_CHECK >= 3
+          for (;;) {  // (re-entered when the list of heavy ligands has no room for this one)
+#endif
           for (;;) {
             const int y = d;
             const uint32_t* pm = mk + ws.moff[slot];
@@ -606,14 +615,16 @@ __global__ void __launch_bounds__(kWarps * 32, PM_FAST_CTAS) pmnet_score_fast_ke
               const int found = ws.lev_start[y] + src;
               const unsigned alive2 = pm[found];
               ++st_nodes;
-              if (args.heavy_budget != 0u && st_nodes > args.heavy_budget && !heavy_denied) {
-                // abandon: the tree is split into tasks (pmnet_score_batch) - if the list has room
+#if PM_FAST_HEAVY_CHECK == 0
+              if (st_nodes > node_limit) {
+                // abandon: the tree is walked by the task rounds (pmnet_score_batch) - if the list has room
                 if (heavy_append(args.workspace, args.heavy_list, args.heavy_acc, lig, lane)) {
                   heavy = true;
                   break;
                 }
-                heavy_denied = true;
+                node_limit = 0xffffffffu;
               }
+#endif
 #if PM_FAST_PREFETCH
               const int myrow = (pf_found == found) ? pf_row : (is_anc ? prow[my_pbase + found] : -1);
               // the next sibling's row indices are requested now (used unless this child is pushed in between)
@@ -673,6 +684,16 @@ __global__ void __launch_bounds__(kWarps * 32, PM_FAST_CTAS) pmnet_score_fast_ke
                 maxm = max(maxm, 2);  // the child returns 1 (a matched leaf) + 1 (itself)
                 continue;
               }
+#if PM_FAST_HEAVY_CHECK == 1
+              if (st_nodes > node_limit) {
+                // abandon: the tree is walked by the task rounds (pmnet_score_batch) - if the list has room
+                if (heavy_append(args.workspace, args.heavy_list, args.heavy_acc, lig, lane)) {
+                  heavy = true;
+                  break;
+                }
+                node_limit = 0xffffffffu;
+              }
+#endif
               // push the child. (depth d + 1's mask slot was last read by other lanes while the previous child's
               // subtree was walked)
               __syncwarp();
@@ -736,8 +757,26 @@ __global__ void __launch_bounds__(kWarps * 32, PM_FAST_CTAS) pmnet_score_fast_ke
               hadc = (sv.z >> 30) & 1u;
               phase = (int)(sv.z >> 31);
               d -= 1;
+#if PM_FAST_HEAVY_CHECK == 3
+              if (st_nodes > node_limit) {
+                heavy = true;
+                break;
+              }
+#elif PM_FAST_HEAVY_CHECK == 4
+              if (d <= 3 && st_nodes > node_limit) {
+                heavy = true;
+                break;
+              }
+#endif
             }
           }
+#if PM_FAST_HEAVY_CHECK >= 3
+            // over the node budget: the tree goes to the task rounds (pmnet_score_batch) - if the list has room
+            if (!heavy || heavy_append(args.workspace, args.heavy_list, args.heavy_acc, lig, lane)) break;
+            heavy = false;
+            node_limit = 0xffffffffu;
+          }
+#endif
           // mean over conformers (graph_match.py:109)
           double s = on ? (double)best : 0.0;
           for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
