@@ -4,7 +4,7 @@
 //   up to 32 conformers (lane = conformer), model tables pinned in shared memory,
 //   per ligand: <= 88 (level, model cluster) entries, <= 32 entries per level, <= 12 levels, <= 224 node-match records
 //   with <= 3 matched model nodes each, <= 48 ligand nodes in the levels, <= 384 mask-stack words, <= 4096 pair
-//   entries and <= 2048 pair-score rows.
+//   entries (their <= 4184 pair-score rows always fit).
 // A ligand outside these caps gets status PMNET_LIG_DEFERRED and is scored by the generic kernel, which
 // pmnet_score_batch enqueues right behind this one on the same stream (status-driven queue, no host round trip).
 //
@@ -46,7 +46,11 @@ constexpr int RC = 224;     // node-match records per ligand
 constexpr int LC = 12;      // levels
 constexpr int NLC = 48;     // ligand nodes in the selected levels
 constexpr int MKW = 384;    // words of the triangular mask stack
-constexpr int ROWS = 2048;  // pair-score rows per warp
+#ifndef PM_FAST_ROWS
+#define PM_FAST_ROWS 4224   // >= PC + TC: a ligand within the other caps can never run out of rows. (With 2048 a few
+#endif                      // ligands per 262 144 were deferred and the general kernel's pass for them - one warp
+                            // each, the GPU idle - cost 2.6 ms per launch)
+constexpr int ROWS = PM_FAST_ROWS;  // pair-score rows per warp
 constexpr int PC = 4096;    // pair entries per warp
 constexpr int kWarps = PM_FAST_WARPS;  // one 1024-thread CTA per SM at 64 registers per thread
 constexpr int kNoBase = INT32_MIN;  // lane a of my_pbase: the node at depth a is a None node (pair bases may be negative)
