@@ -98,9 +98,6 @@ class _Slot:
         self.t = {k: torch.empty(max(1, caps[k]), dtype=dtypes[k], device=device) for k in caps}
         self.ready = torch.cuda.Event()  # H2D finished
         self.free = torch.cuda.Event()  # kernel finished, slot reusable
-        # each slot scores on its own stream with its own scratch, so that the next block's warps back-fill the
-        # SMs while the previous block's longest ligands are still finishing (the tail of a persistent grid)
-        self.stream = torch.cuda.Stream(device)
         self.workspace: torch.Tensor | None = None
         self.order: torch.Tensor | None = None  # longest-first processing order of the block in flight
         self.order_ws: torch.Tensor | None = None
@@ -136,6 +133,13 @@ class Screener:
         # launch shape of the streamed path (None = the library default)
         self.stream_config = stream_config
         self._copy_stream = torch.cuda.Stream(self.device)
+        # Blocks alternate between TWO compute streams (each slot has its own scratch), so that the next block's warps
+        # back-fill the SMs while the previous block's longest ligands are still finishing (the tail of a persistent
+        # grid). Not one stream per slot: the short kernels that end a scoring call (general kernel, task rounds) then
+        # wait behind the persistent kernels other streams have queued - measured: a slot was released two blocks late,
+        # its next copy could not start and the GPU idled 41 ms of a 494 ms pass. With two streams the kernel queued
+        # behind a call's short kernels is always the next block of the SAME stream.
+        self._compute_streams = [torch.cuda.Stream(self.device) for _ in range(2)]
         self._slots: list[_Slot] | None = None
         self._slot_caps: dict[str, int] | None = None
         # optional CUDA-event pairs around every scoring launch (bench.py: kernel duration for the roofline)
@@ -254,22 +258,23 @@ class Screener:
             n_conf += nc
             # the library-wide maximum for every block: one kernel instantiation and one workspace layout per screen
             db = DeviceLigandBatch(views, nb, nc, bases, max_conformers=max(1, lib.max_conformers))
-            if it < self.n_slots:
-                slot.stream.wait_event(start)
-            slot.stream.wait_event(slot.ready)
+            cstream = self._compute_streams[it % 2]
+            if it < 2:
+                cstream.wait_event(start)
+            cstream.wait_event(slot.ready)
             if self.lpt:
                 if slot.order is None or slot.order.numel() < nb:
                     slot.order = torch.empty(max(nb, self.block_ligands), dtype=torch.int32, device=dev)
                     slot.order_ws = torch.empty(
                         int(_lib_order_bytes(max(nb, self.block_ligands))), dtype=torch.uint8, device=dev
                     )
-                cost_order(self.model, db, stream=slot.stream, out=slot.order, workspace=slot.order_ws)
+                cost_order(self.model, db, stream=cstream, out=slot.order, workspace=slot.order_ws)
                 db.set_order(slot.order)
             self._timed_score(
                 db, config=scfg, out_scores=scores[pos : pos + nb], out_status=status[pos : pos + nb],
-                stream=slot.stream, workspace=slot.workspace,
+                stream=cstream, workspace=slot.workspace,
             )  # fmt: skip
-            slot.free.record(slot.stream)
+            slot.free.record(cstream)
             spans.append((pos, nb, a))
             launches += launches_per_call(scfg, max(1, lib.max_conformers)) + int(self.lpt)
             pos += nb
