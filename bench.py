@@ -516,7 +516,8 @@ def run_e2e(args, rank, local_rank, world):
             data.append((image, mask, token_pos, tokens))
         else:
             data.append(None)
-    shard = synthetic.make_library_device(args.e2e_ligands, args.conformers, args.seed + rank, dev, args.templates)
+    shard = synthetic.make_library_device(args.e2e_ligands, args.conformers, args.seed, dev, args.templates,
+                                          coord_seed=args.seed + rank)
     id_base = rank * args.e2e_ligands
     for _ in range(max(1, min(args.warmup, 1))):
         res = pipeline.model_and_screen(net, data, shard, id_base, args.topk, rank, world)
@@ -608,8 +609,9 @@ def main():
     packed = PackedModel.from_model(PharmacophoreModel.load(MODEL_PATH))
     want_ref = rank == 0 and world == 1 and not args.no_cpu_baseline and reference_available()
     n_ref = reference_sample_size(args.ref_seconds, 1, args.conformers) if want_ref else 0
+    # every rank: the same topology set, its own conformers (equal work per rank: weak scaling)
     lib = synthetic.make_library_device(
-        args.ligands, args.conformers, args.seed + rank, dev, args.templates, keep_atoms=n_ref
+        args.ligands, args.conformers, args.seed, dev, args.templates, keep_atoms=n_ref, coord_seed=args.seed + rank
     )
     typed_prefix = lib.typed_prefix
     n_lig, n_conf = lib.n_ligands, lib.n_conformers_total

@@ -271,9 +271,13 @@ def make_library_device(
     flex: float = 0.45,
     noise: float = 0.08,
     keep_atoms: int = 0,
+    coord_seed: int | None = None,
 ):
     """Large synthetic library built on the GPU (benchmarks): `n_templates` topologies from `make_template`, each
     replicated with independently drawn coordinates (same recipe as `make_conformers`, in torch on `device`).
+    `seed` draws the topologies, `coord_seed` (default: `seed`) the coordinates: the shards of several ranks share
+    the topology set and differ in their conformers, so that every rank holds the same amount of work (a random
+    shard of a real library has the same cost distribution as any other; 4096 topologies drawn per rank do not).
     Ligand i uses template i % n_templates, so any prefix of the library is a representative sample.
     Returns a `scoring.DeviceLigandBatch`. Data creation only - nothing here is scored or timed.
     keep_atoms = n (<= n_templates): also keep the ATOM coordinates of the first n ligands and attach them as
@@ -290,7 +294,7 @@ def make_library_device(
     C = int(num_conformers)
     stride = (C + 3) // 4 * 4
     gen = torch.Generator(device=dev)
-    gen.manual_seed(seed)
+    gen.manual_seed(seed if coord_seed is None else coord_seed)
 
     keep_atoms = min(int(keep_atoms), T)
     typed_prefix: list = []
