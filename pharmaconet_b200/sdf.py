@@ -148,6 +148,24 @@ def perceive(rec: MolRecord) -> tuple[AtomTable, list[int]]:
     def bo(a, b):
         return order[(a, b)]
 
+    if n_all == n and n > 0:
+        # A hydrogen-suppressed record (common in vendor libraries): the reference adds polar hydrogens with OpenBabel
+        # (ligand.py: AddPolarHydrogens) before typing. Here: implicit H = standard valence (C 4, N / P 3, O / S 2;
+        # one more for a cation of N / O / P / S, one fewer for any other charge) minus the bond orders, an aromatic
+        # bond (type 4) counting 1.5. Kekule input is exact; with type-4 bonds a pyrrole-type N-H cannot be told from a
+        # pyridine-type N and gets no hydrogen.
+        std = {6: 4, 7: 3, 8: 2, 15: 3, 16: 2}
+        for a in range(n):
+            if z[a] not in std:
+                continue
+            val = std[z[a]]
+            if charge[a] > 0 and z[a] in (7, 8, 15, 16):
+                val += charge[a]
+            elif charge[a] != 0:
+                val -= abs(charge[a])
+            used = sum(1.5 if bo(a, b) == 4 else float(bo(a, b)) for b in nbrs[a])
+            n_h[a] = max(0, int(val - used + 1e-6))
+
     has_double = [any(bo(a, b) == 2 for b in nbrs[a]) for a in range(n)]
     has_triple = [any(bo(a, b) == 3 for b in nbrs[a]) for a in range(n)]
     n_double = [sum(bo(a, b) == 2 for b in nbrs[a]) for a in range(n)]

@@ -76,6 +76,33 @@ def test_functional_groups():
     assert t["Halogen"] == [1] and "HBond_acceptor" not in t
 
 
+def test_hydrogen_suppressed_records_get_implicit_polar_hydrogens():
+    """Vendor libraries usually ship without hydrogens; the reference adds the polar ones (OpenBabel) before typing.
+    Implicit H = standard valence - bond orders: donors are typed without any H atom in the connection table."""
+    # ethanol C-C-O: the hydroxyl donates and accepts
+    _, t = types_of(molblock([("C", 0, 0, 0), ("C", 1.5, 0, 0), ("O", 2.2, 1.0, 0)], [(1, 2, 1), (2, 3, 1)]))
+    assert t["HBond_donor"] == [2] and t["HBond_acceptor"] == [2]
+    # acetamide C-C(=O)-N: the N donates, does not accept; the carbonyl O accepts, does not donate
+    atoms = [("C", 0, 0, 0), ("C", 1.5, 0, 0), ("O", 2.2, 1.0, 0), ("N", 2.2, -1.0, 0)]
+    _, t = types_of(molblock(atoms, [(1, 2, 1), (2, 3, 2), (2, 4, 1)]))
+    assert t["HBond_donor"] == [3] and t["HBond_acceptor"] == [2]
+    # Kekule pyrrole (N with two single ring bonds): aromatic, N-H donates, no acceptor; pyridine: no hydrogen on N
+    atoms, bonds = ring(5, "NCCCC", [1, 2, 1, 2, 1])
+    table, t = types_of(molblock(atoms, bonds))
+    assert t["Aromatic"] == [(0, 1, 2, 3, 4)] and t["HBond_donor"] == [0] and "HBond_acceptor" not in t
+    atoms, bonds = ring(6, "NCCCCC", [2, 1, 2, 1, 2, 1])
+    _, t = types_of(molblock(atoms, bonds))
+    assert t["HBond_acceptor"] == [0] and "HBond_donor" not in t
+    # trimethylammonium cation written without hydrogens and with its charge: one implicit H on N+
+    atoms = [("N", 0, 0, 0), ("C", 1.4, 0, 0), ("C", -0.7, 1.2, 0), ("C", -0.7, -1.2, 0)]
+    _, t = types_of(molblock(atoms, [(1, 2, 1), (1, 3, 1), (1, 4, 1)], charges=[(1, 1)]))
+    assert t["HBond_donor"] == [0] and "HBond_acceptor" not in t
+    # a record WITH explicit hydrogens is taken as complete: ether oxygen next to explicit C-H stays a non-donor
+    atoms = [("C", 0, 0, 0), ("O", 1.4, 0, 0), ("C", 2.8, 0, 0), ("H", -0.5, 0.9, 0)]
+    _, t = types_of(molblock(atoms, [(1, 2, 1), (2, 3, 1), (1, 4, 1)]))
+    assert "HBond_donor" not in t
+
+
 def test_charges_and_conformers(tmp_path):
     # tetramethylammonium (quaternary N, M  CHG line) written as three conformers
     atoms = [("N", 0, 0, 0), ("C", 1, 1, 1), ("C", -1, -1, 1), ("C", -1, 1, -1), ("C", 1, -1, -1)]
