@@ -8,7 +8,8 @@ V2000 file, so that `screening.py` can run on real `.sdf` libraries (BASELINE co
 `examples/library.tar`) without any toolkit:
 
 * one file = one ligand, every record one conformer (ligand.py:63-84); hydrogens are stripped;
-* donors: N / O with at least one attached hydrogen;
+* donors: N / O with at least one attached hydrogen (explicit; for a record without any H atom, implicit from the
+  standard valence minus the bond orders);
 * acceptors: O (neutral or anionic, not in an aromatic ring); N that is neutral, not amide / sulfonamide, not bonded
   to an aromatic ring while carrying hydrogens or three substituents (aniline-like), not an aromatic N with three
   connections (pyrrole-like), and has fewer than four bonds;
