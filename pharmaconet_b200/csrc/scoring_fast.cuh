@@ -38,6 +38,9 @@ namespace fastk {
 #define PM_FAST_HEAVY_CHECK 3  // where the node budget is tested: 0 child created, 1 child pushed, 2 never, 3 node popped (measured:
                                // 69.1 / 70.2 / 71.6 / 72.3 M conformers/s), 4 node popped at depth <= 3
 #endif
+#ifndef PM_FAST_ANC_WIDTH
+#define PM_FAST_ANC_WIDTH 2  // independent row loads per round of the ancestor sums
+#endif
 #ifndef PM_FAST_CTAS
 #define PM_FAST_CTAS 1      // CTAs per SM (PM_FAST_WARPS warps each)
 #endif
@@ -194,12 +197,24 @@ __device__ __forceinline__ int leaf_pass(const WarpS& ws, const float* __restric
       sr_n = ws.srow[nf];
     }
     float t = 0.0f;
+#if PM_FAST_ANC_WIDTH == 4
+    for (int a0 = 1; a0 <= dmax; a0 += 4) {  // four independent row loads per round (lanes > dmax hold -1)
+      const int r0 = __shfl_sync(kFull, myrow, a0), r1 = __shfl_sync(kFull, myrow, a0 + 1);
+      const int r2 = __shfl_sync(kFull, myrow, a0 + 2), r3 = __shfl_sync(kFull, myrow, a0 + 3);
+      const float v0 = (r0 >= 0) ? rows_l[(unsigned)r0 * 32u] : 0.0f;
+      const float v1 = (r1 >= 0) ? rows_l[(unsigned)r1 * 32u] : 0.0f;
+      const float v2 = (r2 >= 0) ? rows_l[(unsigned)r2 * 32u] : 0.0f;
+      const float v3 = (r3 >= 0) ? rows_l[(unsigned)r3 * 32u] : 0.0f;
+      t = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(t, v0), v1), v2), v3);
+    }
+#else
     for (int a0 = 1; a0 <= dmax; a0 += 2) {  // two independent row loads per round (lanes > dmax hold -1)
       const int r0 = __shfl_sync(kFull, myrow, a0), r1 = __shfl_sync(kFull, myrow, a0 + 1);
       const float v0 = (r0 >= 0) ? rows_l[(unsigned)r0 * 32u] : 0.0f;
       const float v1 = (r1 >= 0) ? rows_l[(unsigned)r1 * 32u] : 0.0f;
       t = __fadd_rn(__fadd_rn(t, v0), v1);
     }
+#endif
     const unsigned al = __shfl_sync(kFull, lmw, src);
     if ((al >> lane) & 1u) best = fmaxf(best, __fadd_rn(__fadd_rn(tt, self), t));
     ++nleaf;
@@ -656,12 +671,24 @@ __global__ void __launch_bounds__(kWarps * 32, PM_FAST_CTAS) pmnet_score_fast_ke
               if (sr != 0xffffu) t = __fadd_rn(t, rows_l[sr * 32u]);
               // pair rows with the matched ancestors (tree.py:78-82)
               float acc = 0.0f;
+#if PM_FAST_ANC_WIDTH == 4
+              for (int a0 = 1; a0 <= d; a0 += 4) {  // four independent row loads per round (lanes > d hold -1)
+                const int r0 = __shfl_sync(kFull, myrow, a0), r1 = __shfl_sync(kFull, myrow, a0 + 1);
+                const int r2 = __shfl_sync(kFull, myrow, a0 + 2), r3 = __shfl_sync(kFull, myrow, a0 + 3);
+                const float v0 = (r0 >= 0) ? rows_l[(unsigned)r0 * 32u] : 0.0f;
+                const float v1 = (r1 >= 0) ? rows_l[(unsigned)r1 * 32u] : 0.0f;
+                const float v2 = (r2 >= 0) ? rows_l[(unsigned)r2 * 32u] : 0.0f;
+                const float v3 = (r3 >= 0) ? rows_l[(unsigned)r3 * 32u] : 0.0f;
+                acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v0), v1), v2), v3);
+              }
+#else
               for (int a0 = 1; a0 <= d; a0 += 2) {  // two independent row loads per round (lanes > d hold -1)
                 const int r0 = __shfl_sync(kFull, myrow, a0), r1 = __shfl_sync(kFull, myrow, a0 + 1);
                 const float v0 = (r0 >= 0) ? rows_l[(unsigned)r0 * 32u] : 0.0f;
                 const float v1 = (r1 >= 0) ? rows_l[(unsigned)r1 * 32u] : 0.0f;
                 acc = __fadd_rn(__fadd_rn(acc, v0), v1);
               }
+#endif
               const float tc = __fadd_rn(t, acc);
               if (!anylater) {
                 // no candidate left at any later level: the child's subtree is the chain of None nodes down to the

@@ -157,6 +157,21 @@ def test_streamed_host_screening_equals_single_launch():
     assert np.array_equal(dres.topk_ids.cpu().numpy(), order)
 
 
+@pytest.mark.parametrize("n_slots", [1, 2, 4])
+def test_streamed_screening_any_number_of_staging_slots(n_slots):
+    """Blocks alternate between two compute streams whatever the number of staging slots; a slot is reused only after
+    the kernels that read it have finished (one slot = copy and compute fully serialised)."""
+    from pharmaconet_b200 import screening
+
+    c = load_case("syn0_c8")
+    batch = LigandBatch.from_typed(synthetic.make_ligands(900, 8, seed=79))
+    whole = _run(c["model"], batch, None)["scores"]
+    scr = screening.Screener(c["model"], "cuda:0", k=30, block_ligands=64, n_slots=n_slots)
+    for _ in range(2):
+        res = scr.screen_host(screening.pin_library(batch))
+        assert np.array_equal(res.scores, whole)
+
+
 def test_streamed_screening_reruns_overflow():
     from pharmaconet_b200 import screening
 
