@@ -787,7 +787,10 @@ def main():
                 # ncu --set full capture of the same kernel on 131072 ligands of this workload, scaled per ligand
                 "traffic": (prof["dram_bytes_per_ligand"] * n_lig) if prof else None,
                 "traffic_source": (prof or {}).get("source"),
-                "kernel": "pmnet_score_kernel", "kernel_ms_avg": kernel_ms_avg,
+                # CUDA events around one pmnet_score_batch call on its stream: the specialised kernel is 98 % of it
+                # (profiles/launches_r02_bench_summary.txt), the general / task / finish kernels of the call the rest
+                "kernel": "pmnet_score_fast_kernel (+ the general, task-round and finish kernels of the same call)",
+                "kernel_ms_avg": kernel_ms_avg,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "note": "the path is instruction-issue bound, not HBM bound (DESIGN.md section 5): the HBM fraction "
                         "is reported because BASELINE.json asks for it",
