@@ -103,11 +103,13 @@ constexpr size_t kHeaderBytes = 256;
 // [5] number of deferred ligands, [9] / [16..] / [24..]: the task rounds (kHdrTask*)
 
 // ---------------------------------------------------------------- heavy ligands (task-parallel DFS)
-// A ligand whose tree exceeds `heavy_budget` nodes is abandoned by its warp (status PMNET_LIG_HEAVY) and appended to a
-// list. The task kernel then walks it with MANY warps, in rounds (one launch each):
-//   round 0   one task per heavy ligand: the whole tree. Whenever a walker has created `heavy_budget` nodes since its
-//             last donation it gives away every not yet visited candidate of the SHALLOWEST node on its path that may
-//             be given away, one task per candidate, into the next round's queue, and goes on with what it keeps
+// A ligand whose tree exceeds `heavy_budget` nodes gets a slot in a list of heavy ligands (status PMNET_LIG_HEAVY) and
+// is walked by MANY warps. A walker - the general kernel's warp that has the ligand, or a task warp - that has created
+// `heavy_budget` nodes since it started (then every quarter of it) gives away every not yet visited candidate of the
+// SHALLOWEST node on its path that may be given away, one task per candidate, into the next round's queue, and goes
+// on with what it keeps. The task kernel runs in rounds (one launch each):
+//   round 0   the ligands the SPECIALISED kernel gave up (it has no donation code: it abandons the ligand, and one
+//             task walks the whole tree again)
 //   round r   one warp per donated task {heavy slot, depth j, entries chosen at levels 0..j}: it recomputes phases 0-1
 //             (cheap next to 10^4+ tree nodes), replays the path to the donor's node at depth j with every choice
 //             forced (not counted), walks the subtree below the chosen candidate, donating in turn
@@ -119,8 +121,8 @@ constexpr size_t kHeaderBytes = 256;
 // atomicMax on non-negative floats: exact, order independent) and its node / leaf counts (atomicAdd) into the ligand's
 // accumulator, and pmnet_heavy_finish_kernel writes score, status and statistics - identical to the un-split walk.
 constexpr int kHeavyCap = 65536;   // heavy ligands split per call (more are walked to the end where they are)
-constexpr int kAccWords = 40;      // per heavy ligand: best[32], nodes, leaves, rows, pairs, -
-constexpr int kAccNodes = 32, kAccLeaves = 33, kAccRows = 34, kAccPairs = 35;
+constexpr int kAccWords = 40;      // per heavy ligand: best[32], nodes, leaves, rows, pairs, needs a root task, -
+constexpr int kAccNodes = 32, kAccLeaves = 33, kAccRows = 34, kAccPairs = 35, kAccRoot = 36;
 constexpr int kTaskWords = 32;     // [0] heavy slot, [1] depth j, [4 + i] entry chosen at level i <= j (~0: the None child)
 constexpr int kTaskCap = 1 << 17;  // tasks per round (a full queue: the walker keeps its candidates)
 constexpr int kTaskRounds = 5;
@@ -131,18 +133,19 @@ constexpr int kHdrTaskCount = 16;  // header word 16 + r: tasks queued for round
 constexpr int kHdrTaskHead = 24;   // header word 24 + r: queue position of round r
 constexpr int kHdrTaskBad = 9;     // diagnostics: tasks whose replayed path did not match (must stay 0)
 
-// Claim a slot of the heavy list for `lig` (whole warp; false: the list is full) and clear its accumulator.
-__device__ __forceinline__ bool heavy_append(unsigned char* workspace, uint32_t* heavy_list, uint32_t* heavy_acc,
-                                             uint32_t lig, int lane) {
+// Claim a slot of the heavy list for `lig` (whole warp; -1: the list is full) and clear its accumulator. `root` = the
+// warp gives the ligand up: round 0 walks its whole tree (else the warp keeps walking and only donates).
+__device__ __forceinline__ int heavy_append(unsigned char* workspace, uint32_t* heavy_list, uint32_t* heavy_acc,
+                                            uint32_t lig, int lane, bool root) {
   unsigned hi = 0;
   if (lane == 0) hi = atomicAdd((unsigned int*)workspace + 1, 1u);
   hi = __shfl_sync(0xffffffffu, hi, 0);
-  if (hi >= (unsigned)kHeavyCap) return false;
+  if (hi >= (unsigned)kHeavyCap) return -1;
   if (lane == 0) heavy_list[hi] = lig;
   uint32_t* acc = heavy_acc + (size_t)hi * kAccWords;
   acc[lane] = 0u;
-  if (lane < kAccWords - 32) acc[32 + lane] = 0u;
-  return true;
+  if (lane < kAccWords - 32) acc[32 + lane] = (lane == kAccRoot - 32 && root) ? 1u : 0u;
+  return (int)hi;
 }
 
 // Ligands the specialised kernel defers are appended to a list (when the call has at most this many ligands) so that
@@ -369,6 +372,7 @@ template <int W, bool TG, bool TK = false>
 __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_kernel(const KernelArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int CW = 32 * W;  // conformer slots per row
+  constexpr bool DON = TK || W == 1;  // this instantiation can donate subtrees to the task rounds
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
@@ -466,6 +470,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
         if (nh > (unsigned)kHeavyCap) nh = kHeavyCap;
         if (t >= nh) break;
         task_h = t;
+        if (args.heavy_acc[(size_t)t * kAccWords + kAccRoot] == 0u) continue;  // its warp kept walking: no root task
       } else {
         unsigned nt = ((const unsigned int*)args.workspace)[kHdrTaskCount + args.task_round];
         if (nt > (unsigned)kTaskCap) nt = kTaskCap;
@@ -536,8 +541,8 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
 #pragma unroll
     for (int w = 0; w < W; ++w) best[w] = 0.0f;
     bool task_bad = false;      // TK: the replayed path did not match the donor's (never: diagnostics only)
-    bool heavy = false;         // the tree exceeded the node budget: abandoned, to be split into tasks
-    bool heavy_denied = false;  // the list of heavy ligands is full: walk the tree to the end here
+    bool heavy = false;         // !TK: the ligand has a slot in the heavy list (this warp donates; results go there)
+    bool heavy_denied = false;  // !TK: the list of heavy ligands is full: walk the tree to the end here
 
     if (C < 1 || C > CW) {
       status = PMNET_LIG_UNSUPPORTED;
@@ -999,7 +1004,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
               st_nodes += nleaf;
               st_leaves += nleaf;
               const int nmatch = __shfl_sync(kFull, st_nmatch, d);
-              if (TK && nleaf > 0 && nmatch + 1 >= PMNET_MIN_MATCHES) deep |= (2u << d) - 1u;
+              if (DON && nleaf > 0 && nmatch + 1 >= PMNET_MIN_MATCHES) deep |= (2u << d) - 1u;
               if (lane == d) st_maxm = nleaf > 0 ? 1 : 0;
               if (nleaf == 0 || nmatch + 1 < PMNET_MIN_MATCHES) {
                 // the None leaf (tree.py:98)
@@ -1046,20 +1051,25 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
               if (found >= 0) {
                 // ---- matched child (y, found): ClusterMatchTree.__init__ (tree.py:33-41); it is not a leaf
                 if (!(TK && d < task_j)) ++st_nodes;
-                if (!TK && args.heavy_budget != 0u && st_nodes > args.heavy_budget && !heavy_denied) {
-                  // abandon: the tree is walked by the task kernel (pmnet_score_batch) - if the list has room
-                  if (heavy_append(args.workspace, args.heavy_list, args.heavy_acc, lig, lane)) {
-                    heavy = true;
-                    break;
-                  }
-                  heavy_denied = true;
-                }
                 if (lane == d) {
                   st_cursor = forced ? end : found + 1;
                   st_nchild += 1;
                 }
-                if (TK && __shfl_sync(kFull, st_nmatch, d) + 1 >= PMNET_MIN_MATCHES) deep |= (2u << d) - 1u;
-                if (TK && args.heavy_budget != 0u && d > task_j && st_nodes - mark > grain) {
+                if (DON && __shfl_sync(kFull, st_nmatch, d) + 1 >= PMNET_MIN_MATCHES) deep |= (2u << d) - 1u;
+                bool donate = DON && args.heavy_budget != 0u && d > task_j && st_nodes - mark > grain && !heavy_denied;
+                if (donate && !TK && !heavy) {
+                  // first time over the budget: the ligand needs a slot in the heavy list (its results go there)
+                  const int hi = heavy_append(args.workspace, args.heavy_list, args.heavy_acc, lig, lane, false);
+                  if (hi < 0) {
+                    heavy_denied = true;
+                    donate = false;
+                  } else {
+                    heavy = true;
+                    task_h = (unsigned)hi;
+                    task_acc = args.heavy_acc + (size_t)hi * kAccWords;
+                  }
+                }
+                if (donate) {
                   // ---- donate the unvisited candidates of the shallowest node that may give them away
                   mark = st_nodes;
                   const int pe = __shfl_sync(kFull, st_entry, (lane - 3) & 31);  // lane 4 + i: the entry chosen at level i
@@ -1227,7 +1237,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
                   }
                   st_nodes += nleaf;
                   st_leaves += nleaf;
-                  if (TK && nmatch + 1 >= PMNET_MIN_MATCHES) deep |= (2u << d) - 1u;  // (nleaf > 0 here)
+                  if (DON && nmatch + 1 >= PMNET_MIN_MATCHES) deep |= (2u << d) - 1u;  // (nleaf > 0 here)
                   if (nmatch + 1 < PMNET_MIN_MATCHES) {
                     // the child's None leaf (tree.py:98: too few matches on the path)
                     ++st_nodes;
@@ -1253,7 +1263,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
                 }
 #pragma unroll
                 for (int w = 0; w < W; ++w) tot_l[(d + 1) * CW + 32 * w] = t[w] + acc[w];
-                if (TK) deep = (deep & ((2u << d) - 1u)) | (nmatch >= PMNET_MIN_MATCHES ? (2u << d) : 0u);
+                if (DON) deep = (deep & ((2u << d) - 1u)) | (nmatch >= PMNET_MIN_MATCHES ? (2u << d) : 0u);
                 if (lane == d + 1) {
                   st_cursor = end;
                   st_maxm = 0;
@@ -1279,7 +1289,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
               if (forced ? forced_p < 0 : (nchild == 0 || nmatch + maxm < PMNET_MIN_MATCHES)) {
                 // the None child is not a leaf here (y < L - 1): same masks and totals, one level down
                 if (!forced) ++st_nodes;
-                if (TK) deep = (deep & ((2u << d) - 1u)) | (nmatch >= PMNET_MIN_MATCHES ? (2u << d) : 0u);
+                if (DON) deep = (deep & ((2u << d) - 1u)) | (nmatch >= PMNET_MIN_MATCHES ? (2u << d) : 0u);
                 if (lane == d) st_phase = 1;
                 unsigned alive[W];
 #pragma unroll
@@ -1339,6 +1349,15 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
       continue;
     }
     if (heavy) {
+      // this warp donated parts of the tree: its own part is folded into the accumulator like a task's, and
+      // pmnet_heavy_finish_kernel writes the ligand's outputs after the last round (W == 1)
+      atomicMax((int*)task_acc + lane, __float_as_int(best[0]));
+      if (lane == 0) {
+        atomicAdd(task_acc + kAccNodes, st_nodes);
+        atomicAdd(task_acc + kAccLeaves, st_leaves);
+        task_acc[kAccRows] = st_rows;
+        task_acc[kAccPairs] = st_pairs;
+      }
       status = PMNET_LIG_HEAVY;
       score_out = 0.0f;
     }

@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(kWarps * 32, PM_FAST_CTAS) pmnet_score_fast_ke
 #if PM_FAST_HEAVY_CHECK == 0
               if (st_nodes > node_limit) {
                 // abandon: the tree is walked by the task rounds (pmnet_score_batch) - if the list has room
-                if (heavy_append(args.workspace, args.heavy_list, args.heavy_acc, lig, lane)) {
+                if (heavy_append(args.workspace, args.heavy_list, args.heavy_acc, lig, lane, true) >= 0) {
                   heavy = true;
                   break;
                 }
@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(kWarps * 32, PM_FAST_CTAS) pmnet_score_fast_ke
 #if PM_FAST_HEAVY_CHECK == 1
               if (st_nodes > node_limit) {
                 // abandon: the tree is walked by the task rounds (pmnet_score_batch) - if the list has room
-                if (heavy_append(args.workspace, args.heavy_list, args.heavy_acc, lig, lane)) {
+                if (heavy_append(args.workspace, args.heavy_list, args.heavy_acc, lig, lane, true) >= 0) {
                   heavy = true;
                   break;
                 }
@@ -803,7 +803,7 @@ __global__ void __launch_bounds__(kWarps * 32, PM_FAST_CTAS) pmnet_score_fast_ke
           }
 #if PM_FAST_HEAVY_CHECK >= 3
             // over the node budget: the tree goes to the task rounds (pmnet_score_batch) - if the list has room
-            if (!heavy || heavy_append(args.workspace, args.heavy_list, args.heavy_acc, lig, lane)) break;
+            if (!heavy || heavy_append(args.workspace, args.heavy_list, args.heavy_acc, lig, lane, true) >= 0) break;
             heavy = false;
             node_limit = 0xffffffffu;
           }
