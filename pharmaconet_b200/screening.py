@@ -3,10 +3,12 @@
 
 * one process per GPU; the library is cut into blocks of `block_ligands` ligands and block b belongs to rank
   b mod world (interleaving evens out the DFS-cost variance between regions of a library);
-* host-resident libraries stream through three device staging slots (each with its own stream and scratch): the copies
+* host-resident libraries stream through three device staging slots (each with its own scratch; blocks alternate
+  between two compute streams): the copies
   of the next blocks (pinned host -> HBM, on a copy stream) overlap the scoring kernels of the earlier ones, and the next
   block's warps back-fill the SMs while the previous block's longest ligands finish (measured on one B200, 1 M ligands:
-  61.4 M conformers/s end to end with 2 slots of 131 072 ligands, 64.9 M with 3 slots of 262 144);
+  61.4 M conformers/s end to end with 2 slots of 131 072 ligands, 64.9 M with 3 slots of 262 144, 69.5 M with two
+  compute streams instead of one per slot);
 * every rank keeps the k best (score, ligand id) of its shard; the only collective is one all-gather of those
   k pairs per rank, followed by the same merge on every rank (descending score, ties by ascending id - what
   sorting the reference's full result list gives for its head).
@@ -126,7 +128,7 @@ class Screener:
         self.k = int(k)
         self.config = config or ScoreConfig()
         self.block_ligands = int(block_ligands)
-        self.n_slots = max(2, int(n_slots))  # device staging buffers (each with its own stream and scratch)
+        self.n_slots = max(2, int(n_slots))  # device staging buffers (each with its own scratch)
         self.ramp = bool(ramp)
         # hand ligands to the warps longest first (scoring.cost_order): removes the end-of-launch tail
         self.lpt = bool(lpt)
