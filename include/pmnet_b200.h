@@ -124,10 +124,11 @@ typedef struct PmScoreConfig {
                                 this PMNET_LIG_* code are scored (the others keep score and status): re-running the
                                 PMNET_LIG_OVERFLOW ligands of a previous call with a larger scratch needs no host copy
                                 of the library and no compaction */
-  int32_t heavy_budget;      /* tree nodes after which one warp stops walking a ligand and the same call splits its tree
-                                over many warps (one task per pair of level-0 / level-1 entries); 0: default 262144,
-                                < 0: never split. Only with max_conformers <= 32 and rescore_status == 0. Scores,
-                                per-conformer scores and tree statistics do not depend on it */
+  int32_t heavy_budget;      /* tree nodes after which a ligand's tree is shared out: the warp walking it (and every
+                                warp that takes a piece) gives unvisited subtrees away to a task queue served inside
+                                the same call; 0: default 65536, < 0: never. Only with max_conformers <= 32 and
+                                rescore_status == 0. Scores, per-conformer scores and tree statistics do not depend
+                                on it */
   int32_t reserved[2];
 } PmScoreConfig;
 
@@ -149,9 +150,9 @@ size_t pmnet_score_workspace_bytes(int32_t n_model_nodes, int32_t n_model_cluste
  * per-ligand tables in shared memory; csrc/scoring_fast.cuh) and, behind it, the general one for the ligands the first
  * left PMNET_LIG_DEFERRED. Both compute the same fp32 operations in the same order: results do not depend on which one
  * scored a ligand. An explicit warps_per_block / blocks / scratch_rows selects the general kernel alone.
- * Unless heavy_budget < 0, three more (normally empty) launches follow: the task kernel that walks the trees larger
- * than heavy_budget with one warp per (level-0 entry, level-1 entry) subtree, the kernel that merges the task records,
- * and the general kernel once more for heavy ligands whose tree cannot be split that way.
+ * Unless heavy_budget < 0, four more (normally empty) launches follow: three of the task kernel, which walks the trees
+ * larger than heavy_budget with many warps (walkers donate subtrees to a queue, idle warps take them), and the kernel
+ * that writes the outputs of those ligands.
  */
 int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const float* weights,
                       float* out_scores, float* out_conf_scores, int32_t* out_status, uint32_t* out_stats,

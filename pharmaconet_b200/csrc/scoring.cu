@@ -107,13 +107,15 @@ constexpr size_t kHeaderBytes = 256;
 // is walked by MANY warps. A walker - the general kernel's warp that has the ligand, or a task warp - that has created
 // `heavy_budget` nodes since it started (then every quarter of it) gives away every not yet visited candidate of the
 // SHALLOWEST node on its path that may be given away, one task per candidate, into the next round's queue, and goes
-// on with what it keeps. The task kernel runs in rounds (one launch each):
-//   round 0   the ligands the SPECIALISED kernel gave up (it has no donation code: it abandons the ligand, and one
-//             task walks the whole tree again)
-//   round r   one warp per donated task {heavy slot, depth j, entries chosen at levels 0..j}: it recomputes phases 0-1
-//             (cheap next to 10^4+ tree nodes), replays the path to the donor's node at depth j with every choice
-//             forced (not counted), walks the subtree below the chosen candidate, donating in turn
-//   the last round walks what it gets to the end.
+// on with what it keeps. The queue is consumed by the task kernel (the general kernel's code behind a task queue):
+//   * first the ligands the SPECIALISED kernel gave up (it has no donation code: it abandons the ligand, and one task
+//     walks the whole tree again), then the queue, one warp per task {heavy slot, depth j, entries chosen at levels
+//     0..j}: the warp recomputes phases 0-1 (cheap next to 10^4+ tree nodes), replays the path to the donor's node at
+//     depth j with every choice forced (not counted) and walks the subtree below the chosen candidate, donating in turn
+//     INTO THE SAME QUEUE: a warp that runs out of tasks waits (nanosleep polling, bounded) while any walker of the
+//     launch is still active and takes what they give away - work stealing inside one persistent launch
+//   * the launch is repeated (kTaskRounds in all: what a bounded wait or a full queue left over); the last one does
+//     not donate and walks everything it gets to the end.
 // A node may give its remaining candidates away only when its None child (tree.py:98: nothing matched, or fewer than 5
 // matches on the best path through it) is already ruled out, and with it the None children of all its ancestors: that
 // holds as soon as a node with >= 5 matches on its path has been created below it (`deep` bit per depth). Then no
@@ -124,14 +126,17 @@ constexpr int kHeavyCap = 65536;   // heavy ligands split per call (more are wal
 constexpr int kAccWords = 40;      // per heavy ligand: best[32], nodes, leaves, rows, pairs, needs a root task, -
 constexpr int kAccNodes = 32, kAccLeaves = 33, kAccRows = 34, kAccPairs = 35, kAccRoot = 36;
 constexpr int kTaskWords = 32;     // [0] heavy slot, [1] depth j, [4 + i] entry chosen at level i <= j (~0: the None child)
-constexpr int kTaskCap = 1 << 17;  // tasks per round (a full queue: the walker keeps its candidates)
-constexpr int kTaskRounds = 5;
+constexpr int kTaskCap = 1 << 18;  // tasks per call (a full queue: the walker keeps its candidates)
+constexpr int kTaskRounds = 3;
+constexpr int kTaskMaxSpins = 200000;  // ~0.2 s of polling before an idle warp gives up (the next launch takes over)
 constexpr size_t kHeavyBytes =
-    ((size_t)kHeavyCap * 4 * (1 + kAccWords) + 2 * (size_t)kTaskCap * kTaskWords * 4 + 255) / 256 * 256;
+    ((size_t)kHeavyCap * 4 * (1 + kAccWords) + (size_t)kTaskCap * (kTaskWords + 1) * 4 + 255) / 256 * 256;
 constexpr uint32_t kDefaultHeavyBudget = 1u << 16;
-constexpr int kHdrTaskCount = 16;  // header word 16 + r: tasks queued for round r (r >= 1)
-constexpr int kHdrTaskHead = 24;   // header word 24 + r: queue position of round r
-constexpr int kHdrTaskBad = 9;     // diagnostics: tasks whose replayed path did not match (must stay 0)
+constexpr int kHdrTaskCount = 16;   // header word: task slots reserved so far
+constexpr int kHdrTaskHead = 24;    // header word: tasks taken so far
+constexpr int kHdrTaskActive = 10;  // header word: walkers of the running task launch
+constexpr int kHdrRootHead = 3;     // header word: queue position over the heavy list (root tasks)
+constexpr int kHdrTaskBad = 9;      // diagnostics: tasks that could not be replayed (must stay 0)
 
 // Claim a slot of the heavy list for `lig` (whole warp; -1: the list is full) and clear its accumulator. `root` = the
 // warp gives the ligand up: round 0 walks its whole tree (else the warp keeps walking and only donates).
@@ -227,7 +232,8 @@ struct KernelArgs {
   uint32_t heavy_budget;   // tree nodes after which a ligand is abandoned as PMNET_LIG_HEAVY (0: never)
   uint32_t* heavy_list;    // [kHeavyCap] ligand indices (count in header word 1)
   uint32_t* heavy_acc;     // [kHeavyCap][kAccWords]
-  uint32_t* task_buf[2];   // [kTaskCap][kTaskWords] each: round r reads buf[r & 1] and fills buf[(r + 1) & 1]
+  uint32_t* task_buf;      // [kTaskCap][kTaskWords] task descriptors
+  uint32_t* task_ready;    // [kTaskCap] set (after a fence) once the descriptor is complete; zeroed by every call
   int task_round;          // task kernel: 0 .. kTaskRounds - 1
   WarpLayout ly;    // computed once on the host: the kernel reads the offsets from the constant bank
   const float4* edge_g;  // large models: the edge table in the workspace (build_edge_table_kernel)
@@ -381,7 +387,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
   if (TK) {
     // nothing queued for this round (the normal case): return before the model is loaded
     const unsigned int* hdr = (const unsigned int*)args.workspace;
-    if ((args.task_round == 0 ? hdr[1] : hdr[kHdrTaskCount + args.task_round]) == 0u) return;
+    if (hdr[1] == 0u || (args.task_round != 0 && hdr[kHdrTaskHead] >= min(hdr[kHdrTaskCount], (unsigned)kTaskCap))) return;
   }
 
   // ---- carve shared memory and load the model (once per block)
@@ -455,6 +461,8 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
   // matches, and works through them one by one
   unsigned pend = 0;
   unsigned pend_lig = 0;
+  bool task_active = false;                 // TK: this warp is counted in the header's walker count
+  bool roots_left = args.task_round == 0;   // TK: the heavy list may still hold ligands that need a root task
   for (;;) {
     unsigned int lig = 0;
     int task_j = -1;         // TK: depth of the donor's node whose candidate this task walks (-1: the whole tree)
@@ -462,20 +470,69 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
     unsigned task_word = 0;  // TK: lane l holds word l of the task descriptor
     uint32_t* task_acc = nullptr;
     if (TK) {
-      unsigned t = 0;
-      if (lane == 0) t = atomicAdd((unsigned int*)args.workspace + kHdrTaskHead + args.task_round, 1u);
-      t = __shfl_sync(kFull, t, 0);
-      if (args.task_round == 0) {
-        unsigned nh = ((const unsigned int*)args.workspace)[1];
+      unsigned int* const hdr = (unsigned int*)args.workspace;
+      if (task_active) {  // the previous task of this warp is finished
+        if (lane == 0) atomicSub(hdr + kHdrTaskActive, 1u);
+        task_active = false;
+      }
+      unsigned t = 0xffffffffu;
+      bool is_root = false;
+      if (roots_left) {
+        // the ligands the specialised kernel gave up (first launch only)
+        unsigned nh = hdr[1];
         if (nh > (unsigned)kHeavyCap) nh = kHeavyCap;
-        if (t >= nh) break;
+        for (;;) {
+          if (lane == 0) t = atomicAdd(hdr + kHdrRootHead, 1u);
+          t = __shfl_sync(kFull, t, 0);
+          if (t >= nh) {
+            roots_left = false;
+            t = 0xffffffffu;
+            break;
+          }
+          if (args.heavy_acc[(size_t)t * kAccWords + kAccRoot] != 0u) {
+            is_root = true;
+            break;
+          }
+        }
+      }
+      if (!is_root) {
+        // the task queue; walkers of this launch (heavy_budget != 0) may still add to it
+        if (lane == 0) {
+          volatile unsigned int* const vh = hdr;
+          for (int spins = 0;;) {
+            const unsigned h = vh[kHdrTaskHead];
+            const unsigned c = min(vh[kHdrTaskCount], (unsigned)kTaskCap);
+            if (h < c) {
+              if (atomicCAS(hdr + kHdrTaskHead, h, h + 1u) == h) {
+                t = h;
+                break;
+              }
+              continue;
+            }
+            if (args.heavy_budget == 0u || vh[kHdrTaskActive] == 0u || ++spins > kTaskMaxSpins) break;
+            __nanosleep(1000);
+          }
+          if (t != 0xffffffffu) {
+            // the donor reserved the slot first and publishes the descriptor right after
+            volatile unsigned int* const rdy = args.task_ready + t;
+            for (int spins = 0; *rdy == 0u && spins < (1 << 22); ++spins) __nanosleep(100);
+            if (*rdy == 0u) {
+              atomicAdd(hdr + kHdrTaskBad, 1u);
+              t = 0xfffffffeu;  // (cannot happen) skip it
+            }
+            __threadfence();
+          }
+        }
+        t = __shfl_sync(kFull, t, 0);
+        if (t == 0xffffffffu) break;
+        if (t == 0xfffffffeu) continue;
+      }
+      if (lane == 0) atomicAdd(hdr + kHdrTaskActive, 1u);
+      task_active = true;
+      if (is_root) {
         task_h = t;
-        if (args.heavy_acc[(size_t)t * kAccWords + kAccRoot] == 0u) continue;  // its warp kept walking: no root task
       } else {
-        unsigned nt = ((const unsigned int*)args.workspace)[kHdrTaskCount + args.task_round];
-        if (nt > (unsigned)kTaskCap) nt = kTaskCap;
-        if (t >= nt) break;
-        task_word = args.task_buf[args.task_round & 1][(size_t)t * kTaskWords + lane];
+        task_word = __ldcg(args.task_buf + (size_t)t * kTaskWords + lane);
         task_h = __shfl_sync(kFull, task_word, 0);
         task_j = (int)__shfl_sync(kFull, task_word, 1);
       }
@@ -1078,8 +1135,8 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
                   // ---- donate the unvisited candidates of the shallowest node that may give them away
                   mark = st_nodes;
                   const int pe = __shfl_sync(kFull, st_entry, (lane - 3) & 31);  // lane 4 + i: the entry chosen at level i
-                  unsigned int* const qcount = (unsigned int*)args.workspace + kHdrTaskCount + args.task_round + 1;
-                  uint32_t* const qout = args.task_buf[(args.task_round + 1) & 1];
+                  unsigned int* const qcount = (unsigned int*)args.workspace + kHdrTaskCount;
+                  uint32_t* const qout = args.task_buf;
                   for (int s = task_j + 1; s <= d; ++s) {
                     if (!((deep >> s) & 1u)) continue;
                     const int cs = __shfl_sync(kFull, st_cursor, s), es = ws.lev_start[s + 1];
@@ -1120,6 +1177,9 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
                         else if (lane >= 4 && lane - 4 < s) wv = (uint32_t)pe;
                         else if (lane - 4 == s) wv = (uint32_t)c;
                         qout[(size_t)base * kTaskWords + lane] = wv;
+                        __threadfence();  // the descriptor before its ready flag
+                        __syncwarp();
+                        if (lane == 0) *(volatile uint32_t*)(args.task_ready + base) = 1u;
                         ++base;
                       }
                     }
@@ -1586,13 +1646,14 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
   a.heavy_budget = W == 1 ? heavy_budget_of(cfg) : 0u;
   a.heavy_list = (uint32_t*)((unsigned char*)workspace + scratch_bytes(model->n_nodes, model->n_clusters, cfg));
   a.heavy_acc = a.heavy_list + kHeavyCap;
-  a.task_buf[0] = a.heavy_acc + (size_t)kHeavyCap * kAccWords;
-  a.task_buf[1] = a.task_buf[0] + (size_t)kTaskCap * kTaskWords;
+  a.task_buf = a.heavy_acc + (size_t)kHeavyCap * kAccWords;
+  a.task_ready = a.task_buf + (size_t)kTaskCap * kTaskWords;
   a.task_round = 0;
   a.list = nullptr;
   a.list_count_word = 0;
   a.list_cap = 0;
   e = cudaMemsetAsync(workspace, 0, kHeaderBytes, stream);
+  if (e == cudaSuccess && a.heavy_budget != 0u) e = cudaMemsetAsync(a.task_ready, 0, (size_t)kTaskCap * 4, stream);
   if (e != cudaSuccess) {
     set_err(cudaGetErrorString(e));
     return PMNET_ECUDA;

@@ -67,7 +67,7 @@ for b in [int(x) for x in a.budgets.split(",")]:
             print(f"    ligand {i}: phases 0-1 {t01[i]:.0f} us, DFS {t2[i]:.0f} us, nodes {nodes[i]:.0f}, leaves {stats[i, 1]:.0f}")
     if a.profile and nh > 0:
         hdr = ws[:256].view(torch.int32).cpu().numpy()
-        print(f"  tasks donated to rounds 1..4: {hdr[17:21].tolist()}, replay mismatches {hdr[9]}, deferred {hdr[5]}")
+        print(f"  tasks donated {hdr[16]}, taken {hdr[24]}, replay failures {hdr[9]}, deferred {hdr[5]}")
         from torch.profiler import ProfilerActivity, profile
 
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
