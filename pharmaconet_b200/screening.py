@@ -130,6 +130,7 @@ class Screener:
         self.block_ligands = int(block_ligands)
         self.n_slots = max(2, int(n_slots))  # device staging buffers (each with its own scratch)
         self.ramp = bool(ramp)
+        self.ramp_cuts = (0.125, 0.25, 0.5)  # cumulative fractions of the first block where it is cut
         # hand ligands to the warps longest first (scoring.cost_order): removes the end-of-launch tail
         self.lpt = bool(lpt)
         # launch shape of the streamed path (None = the library default)
@@ -223,8 +224,8 @@ class Screener:
         if self.ramp and blocks and blocks[0][1] - blocks[0][0] >= 8192:
             a0, b0 = blocks[0]
             n0 = b0 - a0
-            cuts = [a0, a0 + n0 // 8, a0 + n0 // 4, a0 + n0 // 2, b0]
-            blocks = [(cuts[i], cuts[i + 1]) for i in range(4)] + blocks[1:]
+            cuts = [a0] + [a0 + int(n0 * f) for f in self.ramp_cuts] + [b0]
+            blocks = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)] + blocks[1:]
         scores = torch.empty(n_mine, dtype=torch.float32, device=dev)
         status = torch.empty(n_mine, dtype=torch.int32, device=dev)
         cand_s, cand_i = [], []

@@ -19,6 +19,7 @@ ap.add_argument("--block-ligands", type=int, default=262144)
 ap.add_argument("--slots", type=int, default=3)
 ap.add_argument("--no-ramp", action="store_true")
 ap.add_argument("--min-us", type=float, default=300.0)
+ap.add_argument("--ramp-cuts", type=str, default="")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 packed = PackedModel.from_model(PharmacophoreModel.load(os.path.join(ROOT, "tests", "golden", "model_syn0.pm")))
@@ -27,6 +28,8 @@ host = screening.pin_library(LigandBatch.from_arrays({k: v.cpu().numpy() for k, 
 del lib
 torch.cuda.empty_cache()
 scr = screening.Screener(packed, dev, k=1000, block_ligands=a.block_ligands, n_slots=a.slots, ramp=not a.no_ramp)
+if a.ramp_cuts:
+    scr.ramp_cuts = tuple(float(x) for x in a.ramp_cuts.split(","))
 for _ in range(2):
     scr.screen_host(host)
 torch.cuda.synchronize()
