@@ -38,6 +38,16 @@ namespace fastk {
 #define PM_FAST_HEAVY_CHECK 3  // where the node budget is tested: 0 child created, 1 child pushed, 2 never, 3 node popped (measured:
                                // 69.1 / 70.2 / 71.6 / 72.3 M conformers/s), 4 node popped at depth <= 3
 #endif
+#ifndef PM_FAST_ROW_LD
+#define PM_FAST_ROW_LD 0    // how the DFS reads score rows: 0 plain (L1 + L2), 1 ld.global.cg (L2 only), 2 ld.global.cs (streaming)
+#endif
+#if PM_FAST_ROW_LD == 1
+#define PM_ROW_LD(p) __ldcg(p)
+#elif PM_FAST_ROW_LD == 2
+#define PM_ROW_LD(p) __ldcs(p)
+#else
+#define PM_ROW_LD(p) (*(p))
+#endif
 #ifndef PM_FAST_ANC_WIDTH
 #define PM_FAST_ANC_WIDTH 2  // independent row loads per round of the ancestor sums
 #endif
@@ -190,7 +200,7 @@ __device__ __forceinline__ int leaf_pass(const WarpS& ws, const float* __restric
     bal &= bal - 1;
     const int myrow = myrow_n;
     const unsigned sr = sr_n;
-    const float self = (sr != 0xffffu) ? rows_l[sr * 32u] : 0.0f;
+    const float self = (sr != 0xffffu) ? PM_ROW_LD(rows_l + sr * 32u) : 0.0f;
     if (bal) {
       nf = base + __ffs(bal) - 1;
       myrow_n = is_anc ? prow[pb + nf] : -1;
@@ -201,17 +211,17 @@ __device__ __forceinline__ int leaf_pass(const WarpS& ws, const float* __restric
     for (int a0 = 1; a0 <= dmax; a0 += 4) {  // four independent row loads per round (lanes > dmax hold -1)
       const int r0 = __shfl_sync(kFull, myrow, a0), r1 = __shfl_sync(kFull, myrow, a0 + 1);
       const int r2 = __shfl_sync(kFull, myrow, a0 + 2), r3 = __shfl_sync(kFull, myrow, a0 + 3);
-      const float v0 = (r0 >= 0) ? rows_l[(unsigned)r0 * 32u] : 0.0f;
-      const float v1 = (r1 >= 0) ? rows_l[(unsigned)r1 * 32u] : 0.0f;
-      const float v2 = (r2 >= 0) ? rows_l[(unsigned)r2 * 32u] : 0.0f;
-      const float v3 = (r3 >= 0) ? rows_l[(unsigned)r3 * 32u] : 0.0f;
+      const float v0 = (r0 >= 0) ? PM_ROW_LD(rows_l + (unsigned)r0 * 32u) : 0.0f;
+      const float v1 = (r1 >= 0) ? PM_ROW_LD(rows_l + (unsigned)r1 * 32u) : 0.0f;
+      const float v2 = (r2 >= 0) ? PM_ROW_LD(rows_l + (unsigned)r2 * 32u) : 0.0f;
+      const float v3 = (r3 >= 0) ? PM_ROW_LD(rows_l + (unsigned)r3 * 32u) : 0.0f;
       t = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(t, v0), v1), v2), v3);
     }
 #else
     for (int a0 = 1; a0 <= dmax; a0 += 2) {  // two independent row loads per round (lanes > dmax hold -1)
       const int r0 = __shfl_sync(kFull, myrow, a0), r1 = __shfl_sync(kFull, myrow, a0 + 1);
-      const float v0 = (r0 >= 0) ? rows_l[(unsigned)r0 * 32u] : 0.0f;
-      const float v1 = (r1 >= 0) ? rows_l[(unsigned)r1 * 32u] : 0.0f;
+      const float v0 = (r0 >= 0) ? PM_ROW_LD(rows_l + (unsigned)r0 * 32u) : 0.0f;
+      const float v1 = (r1 >= 0) ? PM_ROW_LD(rows_l + (unsigned)r1 * 32u) : 0.0f;
       t = __fadd_rn(__fadd_rn(t, v0), v1);
     }
 #endif
@@ -668,24 +678,24 @@ __global__ void __launch_bounds__(kWarps * 32, PM_FAST_CTAS) pmnet_score_fast_ke
                 anylater |= __any_sync(kFull, more != 0u);
               }
               float t = tot_l[slot * 32];
-              if (sr != 0xffffu) t = __fadd_rn(t, rows_l[sr * 32u]);
+              if (sr != 0xffffu) t = __fadd_rn(t, PM_ROW_LD(rows_l + sr * 32u));
               // pair rows with the matched ancestors (tree.py:78-82)
               float acc = 0.0f;
 #if PM_FAST_ANC_WIDTH == 4
               for (int a0 = 1; a0 <= d; a0 += 4) {  // four independent row loads per round (lanes > d hold -1)
                 const int r0 = __shfl_sync(kFull, myrow, a0), r1 = __shfl_sync(kFull, myrow, a0 + 1);
                 const int r2 = __shfl_sync(kFull, myrow, a0 + 2), r3 = __shfl_sync(kFull, myrow, a0 + 3);
-                const float v0 = (r0 >= 0) ? rows_l[(unsigned)r0 * 32u] : 0.0f;
-                const float v1 = (r1 >= 0) ? rows_l[(unsigned)r1 * 32u] : 0.0f;
-                const float v2 = (r2 >= 0) ? rows_l[(unsigned)r2 * 32u] : 0.0f;
-                const float v3 = (r3 >= 0) ? rows_l[(unsigned)r3 * 32u] : 0.0f;
+                const float v0 = (r0 >= 0) ? PM_ROW_LD(rows_l + (unsigned)r0 * 32u) : 0.0f;
+                const float v1 = (r1 >= 0) ? PM_ROW_LD(rows_l + (unsigned)r1 * 32u) : 0.0f;
+                const float v2 = (r2 >= 0) ? PM_ROW_LD(rows_l + (unsigned)r2 * 32u) : 0.0f;
+                const float v3 = (r3 >= 0) ? PM_ROW_LD(rows_l + (unsigned)r3 * 32u) : 0.0f;
                 acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v0), v1), v2), v3);
               }
 #else
               for (int a0 = 1; a0 <= d; a0 += 2) {  // two independent row loads per round (lanes > d hold -1)
                 const int r0 = __shfl_sync(kFull, myrow, a0), r1 = __shfl_sync(kFull, myrow, a0 + 1);
-                const float v0 = (r0 >= 0) ? rows_l[(unsigned)r0 * 32u] : 0.0f;
-                const float v1 = (r1 >= 0) ? rows_l[(unsigned)r1 * 32u] : 0.0f;
+                const float v0 = (r0 >= 0) ? PM_ROW_LD(rows_l + (unsigned)r0 * 32u) : 0.0f;
+                const float v1 = (r1 >= 0) ? PM_ROW_LD(rows_l + (unsigned)r1 * 32u) : 0.0f;
                 acc = __fadd_rn(__fadd_rn(acc, v0), v1);
               }
 #endif
