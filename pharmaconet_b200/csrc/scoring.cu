@@ -816,9 +816,22 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
         const float* const dist_l = dist + lane;
         float* const rows_l = rows + lane;
         int nrows = 0;
+        // TK: a task only creates the entries of its path (levels <= task_j) and entries of later levels: the rows
+        // of every other entry of the path's levels are never read and are not computed (path_entry(l) = the path's
+        // entry at level l, -1 for a None child, -2 for "no restriction")
+        auto path_entry = [&](int lev) -> int {
+          return (TK && lev <= task_j) ? (int)__shfl_sync(kFull, task_word, 4 + lev) : -2;
+        };
         for (int e = 0; e < T && !overflow; ++e) {
           const int cnt = nmcnt[e];
           int r = -1;
+          if (TK && task_j >= 0) {
+            const int pe_ = path_entry(entlev[e]);
+            if (pe_ != -2 && pe_ != e) {
+              if (lane == 0) srow[e] = -1;
+              continue;
+            }
+          }
           if (cnt >= 2) {
             float sc[W];
             int nf[W];
@@ -857,7 +870,11 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
             cix[w] = gi[32 * w]; ciy[w] = gi[CW + 32 * w]; ciz[w] = gi[2 * CW + 32 * w]; csi[w] = gi[3 * CW + 32 * w];
           }
           const int s1 = ws.lev_start[i], e1_end = ws.lev_start[i + 1];
+          const int only1 = path_entry(i);
+          if (only1 == -1) continue;  // the path takes the None child at this level
           for (int j = i + 1; j < L && !overflow; ++j) {
+            const int only2 = path_entry(j);
+            if (only2 == -1) continue;
             const float* gj = geo + (size_t)j * 4 * CW + lane;
             float ldist[W], lsize[W];
 #pragma unroll
@@ -868,6 +885,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
             }
             const int s2 = ws.lev_start[j], e2_end = ws.lev_start[j + 1];
             for (int e1 = s1; e1 < e1_end && !overflow; ++e1) {
+              if (only1 != -2 && e1 != only1) continue;
               const int k = entmc[e1];
               const int cnt1 = nmcnt[e1];
               const uint32_t off1 = nmoff[e1];
@@ -875,6 +893,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
               const float* cd = sm.cdist + k * KM;
               const float* cs = sm.csize + k * KM;
               for (int e2 = s2; e2 < e2_end; ++e2) {
+                if (only2 != -2 && e2 != only2) continue;
                 const int l = entmc[e2];
                 // cluster prefilter (graph_match.py:263-268): min_c(|d_lig - d_mod| - size_lig) > size_mod
                 const float cdl = cd[l], csl = cs[l];
@@ -1406,8 +1425,10 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
         if (lane == 0) {
           atomicAdd(task_acc + kAccNodes, st_nodes);
           atomicAdd(task_acc + kAccLeaves, st_leaves);
-          task_acc[kAccRows] = st_rows;  // the same in every task of the ligand
-          task_acc[kAccPairs] = st_pairs;
+          if (task_j < 0) {  // (a task with a path has computed only the rows it needs; the donor wrote these)
+            task_acc[kAccRows] = st_rows;
+            task_acc[kAccPairs] = st_pairs;
+          }
         }
       }
       __syncwarp();
