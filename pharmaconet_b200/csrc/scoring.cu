@@ -235,6 +235,7 @@ struct KernelArgs {
   uint32_t* task_buf;      // [kTaskCap][kTaskWords] task descriptors
   uint32_t* task_ready;    // [kTaskCap] set (after a fence) once the descriptor is complete; zeroed by every call
   int task_round;          // task kernel: 0 .. kTaskRounds - 1
+  int ligands_first;       // task kernel, first launch: serve the ligand queue (like the general kernel) before the tasks
   WarpLayout ly;    // computed once on the host: the kernel reads the offsets from the constant bank
   const float4* edge_g;  // large models: the edge table in the workspace (build_edge_table_kernel)
 };
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
   const int warps_per_block = blockDim.x >> 5;
   const PmModel& gm = args.model;
   const int NM = gm.n_nodes, KM = gm.n_clusters;
-  if (TK) {
+  if (TK && !(args.task_round == 0 && args.ligands_first)) {
     // nothing queued for this round (the normal case): return before the model is loaded
     const unsigned int* hdr = (const unsigned int*)args.workspace;
     if (hdr[1] == 0u || (args.task_round != 0 && hdr[kHdrTaskHead] >= min(hdr[kHdrTaskCount], (unsigned)kTaskCap))) return;
@@ -463,20 +464,27 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
   unsigned pend_lig = 0;
   bool task_active = false;                 // TK: this warp is counted in the header's walker count
   bool roots_left = args.task_round == 0;   // TK: the heavy list may still hold ligands that need a root task
+  // TK, first launch: the ligand queue comes first (this launch then replaces the general kernel's; its warps go on
+  // with the tasks as soon as the ligands run out, while others are still walking theirs)
+  bool ligands_left = !TK || (args.task_round == 0 && args.ligands_first != 0);
   for (;;) {
     unsigned int lig = 0;
     int task_j = -1;         // TK: depth of the donor's node whose candidate this task walks (-1: the whole tree)
     unsigned task_h = 0;     // TK: slot of the ligand in the heavy list
     unsigned task_word = 0;  // TK: lane l holds word l of the task descriptor
     uint32_t* task_acc = nullptr;
+    bool is_task = false;    // TK: this item is a task (else a ligand of the queue)
+    bool is_root = false;    // TK: ... the task of a ligand the specialised kernel gave up (its whole tree)
+    unsigned task_slot = 0;  // TK: position of the task in its queue
+    if (TK && task_active) {  // the previous item of this warp is finished
+      if (lane == 0) atomicSub((unsigned int*)args.workspace + kHdrTaskActive, 1u);
+      task_active = false;
+    }
     if (TK) {
+      // tasks first (they are the long donation chains of the heaviest ligands: the earlier they run, the shorter the
+      // launch), ligands when no task is ready; once the ligands are gone, wait for tasks while walkers are active
       unsigned int* const hdr = (unsigned int*)args.workspace;
-      if (task_active) {  // the previous task of this warp is finished
-        if (lane == 0) atomicSub(hdr + kHdrTaskActive, 1u);
-        task_active = false;
-      }
       unsigned t = 0xffffffffu;
-      bool is_root = false;
       if (roots_left) {
         // the ligands the specialised kernel gave up (first launch only)
         unsigned nh = hdr[1];
@@ -509,7 +517,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
               }
               continue;
             }
-            if (args.heavy_budget == 0u || vh[kHdrTaskActive] == 0u || ++spins > kTaskMaxSpins) break;
+            if (ligands_left || args.heavy_budget == 0u || vh[kHdrTaskActive] == 0u || ++spins > kTaskMaxSpins) break;
             __nanosleep(1000);
           }
           if (t != 0xffffffffu) {
@@ -524,11 +532,17 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
           }
         }
         t = __shfl_sync(kFull, t, 0);
-        if (t == 0xffffffffu) break;
         if (t == 0xfffffffeu) continue;
       }
-      if (lane == 0) atomicAdd(hdr + kHdrTaskActive, 1u);
-      task_active = true;
+      if (t != 0xffffffffu) {
+        is_task = true;
+        task_slot = t;
+      } else if (!ligands_left) {
+        break;
+      }
+    }
+    if (TK && is_task) {
+      const unsigned t = task_slot;
       if (is_root) {
         task_h = t;
       } else {
@@ -553,14 +567,22 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
         lig = args.list[t];
         if (args.only_status < 0 || args.out_status[lig] == args.only_status) break;
       }
-      if (done) break;
+      if (done) {
+        if (!TK) break;
+        ligands_left = false;
+        continue;
+      }
     } else if (args.only_status < 0) {
       if (lane == 0) {
         lig = atomicAdd(counter, 1u);
         if (B.order != nullptr && lig < (unsigned)B.n_ligands) lig = (unsigned)B.order[lig];
       }
       lig = __shfl_sync(kFull, lig, 0);
-      if (lig >= (unsigned)B.n_ligands) break;
+      if (lig >= (unsigned)B.n_ligands) {
+        if (!TK) break;
+        ligands_left = false;
+        continue;
+      }
     } else {
       bool done = false;
       while (pend == 0u) {
@@ -579,12 +601,20 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
         }
         pend = __ballot_sync(kFull, mine);
       }
-      if (done) break;
+      if (done) {
+        if (!TK) break;
+        ligands_left = false;
+        continue;
+      }
       const int src = __ffs(pend) - 1;
       pend &= pend - 1;
       lig = __shfl_sync(kFull, pend_lig, src);
     }
 
+    if (TK) {  // a walker of the task launch (it may donate): idle warps wait for it
+      if (lane == 0) atomicAdd((unsigned int*)args.workspace + kHdrTaskActive, 1u);
+      task_active = true;
+    }
     const int C = B.n_conf[lig];
     float score_out = 0.0f;
     int status = PMNET_LIG_OK;
@@ -1138,7 +1168,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
                 }
                 if (DON && __shfl_sync(kFull, st_nmatch, d) + 1 >= PMNET_MIN_MATCHES) deep |= (2u << d) - 1u;
                 bool donate = DON && args.heavy_budget != 0u && d > task_j && st_nodes - mark > grain && !heavy_denied;
-                if (donate && !TK && !heavy) {
+                if (donate && !is_task && !heavy) {
                   // first time over the budget: the ligand needs a slot in the heavy list (its results go there)
                   const int hi = heavy_append(args.workspace, args.heavy_list, args.heavy_acc, lig, lane, false);
                   if (hi < 0) {
@@ -1415,7 +1445,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
       }
       (void)lane_on;
     }
-    if (TK) {
+    if (TK && is_task) {
       // fold the task into the ligand's accumulator (pmnet_heavy_finish_kernel); W == 1
       if (status != PMNET_LIG_OK || task_bad) {
         if (lane == 0) atomicAdd((unsigned int*)args.workspace + kHdrTaskBad, 1u);
@@ -1731,20 +1761,25 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
   if (W == 1) fn = tg ? (const void*)pmnet_score_kernel<1, true> : (const void*)pmnet_score_kernel<1, false>;
   else if (W == 2) fn = tg ? (const void*)pmnet_score_kernel<2, true> : (const void*)pmnet_score_kernel<2, false>;
   else fn = tg ? (const void*)pmnet_score_kernel<4, true> : (const void*)pmnet_score_kernel<4, false>;
-  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) {
-    set_err(cudaGetErrorString(e));
-    return PMNET_ECUDA;
-  }
-  void* kargs[] = {(void*)&a};
-  e = cudaLaunchKernel(fn, dim3(c.blocks), dim3(c.warps_per_block * 32), kargs, smem, stream);
-  if (e != cudaSuccess) {
-    set_err(cudaGetErrorString(e));
-    return PMNET_ECUDA;
-  }
-  if (a.heavy_budget != 0u) {
-    // ---- heavy ligands: the rounds of the task kernel (each returns at once when its queue is empty), then the
-    // kernel that turns the accumulators into scores
+  a.ligands_first = 0;
+  if (a.heavy_budget == 0u) {
+    // ---- the general kernel over the ligand queue (all ligands, the deferred ones, or a status-restricted re-run)
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_err(cudaGetErrorString(e));
+      return PMNET_ECUDA;
+    }
+    void* kargs[] = {(void*)&a};
+    e = cudaLaunchKernel(fn, dim3(c.blocks), dim3(c.warps_per_block * 32), kargs, smem, stream);
+    if (e != cudaSuccess) {
+      set_err(cudaGetErrorString(e));
+      return PMNET_ECUDA;
+    }
+  } else {
+    // ---- the task kernel (the general kernel's code behind a task queue), kTaskRounds launches: the first serves the
+    // ligand queue like the general kernel would, then the ligands the specialised kernel gave up and the task queue
+    // (its walkers donate into the queue it is consuming); the others return at once unless something is left over.
+    // Then the kernel that turns the accumulators of the heavy ligands into scores
     const void* tfn = tg ? (const void*)pmnet_score_kernel<1, true, true> : (const void*)pmnet_score_kernel<1, false, true>;
     e = cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -1753,10 +1788,9 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
     }
     for (int round = 0; round < kTaskRounds; ++round) {
       KernelArgs t = a;
-      t.heavy_budget = round == kTaskRounds - 1 ? 0u : a.heavy_budget;  // the last round walks everything to the end
-      t.only_status = -1;
-      t.list = nullptr;
+      t.heavy_budget = round == kTaskRounds - 1 ? 0u : a.heavy_budget;  // the last launch walks everything to the end
       t.task_round = round;
+      t.ligands_first = round == 0 ? 1 : 0;
       void* targs[] = {(void*)&t};
       e = cudaLaunchKernel(tfn, dim3(c.blocks), dim3(c.warps_per_block * 32), targs, smem, stream);
       if (e != cudaSuccess) {
