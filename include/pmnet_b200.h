@@ -150,9 +150,10 @@ size_t pmnet_score_workspace_bytes(int32_t n_model_nodes, int32_t n_model_cluste
  * per-ligand tables in shared memory; csrc/scoring_fast.cuh) and, behind it, the general one for the ligands the first
  * left PMNET_LIG_DEFERRED. Both compute the same fp32 operations in the same order: results do not depend on which one
  * scored a ligand. An explicit warps_per_block / blocks / scratch_rows selects the general kernel alone.
- * Unless heavy_budget < 0, four more (normally empty) launches follow: three of the task kernel, which walks the trees
- * larger than heavy_budget with many warps (walkers donate subtrees to a queue, idle warps take them), and the kernel
- * that writes the outputs of those ligands.
+ * Unless heavy_budget < 0, the general kernel's work is done by the first of three launches of the task kernel (the
+ * same code behind a task queue: trees larger than heavy_budget are walked by many warps - walkers donate subtrees to
+ * the queue, idle warps take them; the other two launches normally return at once), followed by the kernel that writes
+ * the outputs of those ligands.
  */
 int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const float* weights,
                       float* out_scores, float* out_conf_scores, int32_t* out_status, uint32_t* out_stats,
