@@ -98,22 +98,24 @@ __host__ __device__ inline WarpLayout make_layout(int n_model_clusters, int scra
 }
 
 constexpr size_t kHeaderBytes = 256;
-// header words: [0] queue of the specialised kernel, [1] number of heavy ligands, [2] queue of the general kernel
-// (deferred pass),
-// [5] number of deferred ligands, [9] / [16..] / [24..]: the task rounds (kHdrTask*)
+// header words (zeroed by every call): [0] queue of the specialised kernel, [1] number of heavy ligands, [2] queue of
+// the general kernel's pass over the deferred ligands, [3] queue over the heavy list (root tasks), [5] number of
+// deferred ligands, [9] / [10] / [16] / [24]: the task queue (kHdrTask*)
 
 // ---------------------------------------------------------------- heavy ligands (task-parallel DFS)
 // A ligand whose tree exceeds `heavy_budget` nodes gets a slot in a list of heavy ligands (status PMNET_LIG_HEAVY) and
-// is walked by MANY warps. A walker - the general kernel's warp that has the ligand, or a task warp - that has created
-// `heavy_budget` nodes since it started (then every quarter of it) gives away every not yet visited candidate of the
-// SHALLOWEST node on its path that may be given away, one task per candidate, into the next round's queue, and goes
-// on with what it keeps. The queue is consumed by the task kernel (the general kernel's code behind a task queue):
-//   * first the ligands the SPECIALISED kernel gave up (it has no donation code: it abandons the ligand, and one task
-//     walks the whole tree again), then the queue, one warp per task {heavy slot, depth j, entries chosen at levels
-//     0..j}: the warp recomputes phases 0-1 (cheap next to 10^4+ tree nodes), replays the path to the donor's node at
-//     depth j with every choice forced (not counted) and walks the subtree below the chosen candidate, donating in turn
-//     INTO THE SAME QUEUE: a warp that runs out of tasks waits (nanosleep polling, bounded) while any walker of the
-//     launch is still active and takes what they give away - work stealing inside one persistent launch
+// is walked by MANY warps. A walker - the warp that has the ligand, or a task warp - that has created `heavy_budget`
+// nodes since it started (half of it for a task; then every quarter of it) gives away every not yet visited candidate
+// of the SHALLOWEST node on its path that may be given away, one task per candidate, into the task queue, and goes on
+// with what it keeps. The queue is consumed by the task kernel (TK = the general kernel's code behind a task queue):
+//   * its first launch is also the general kernel's pass over the ligand queue. A warp takes, in this order: a ligand
+//     the SPECIALISED kernel gave up (it has no donation code: it abandons the ligand, and one "root" task walks the
+//     whole tree again); a ready task; the next ligand of the queue; and once the ligands are gone it waits for tasks
+//     (nanosleep polling, bounded) while any walker of the launch is still active - work stealing inside one
+//     persistent launch. Tasks before ligands: the donation chains of the heaviest ligands bound the launch
+//   * a task {heavy slot, depth j, entries chosen at levels 0..j}: the warp recomputes phase 0 and the part of phase 1
+//     its subtree can reach, replays the path to the donor's node at depth j with every choice forced (not counted)
+//     and walks the subtree below the chosen candidate, donating in turn into the same queue
 //   * the launch is repeated (kTaskRounds in all: what a bounded wait or a full queue left over); the last one does
 //     not donate and walks everything it gets to the end.
 // A node may give its remaining candidates away only when its None child (tree.py:98: nothing matched, or fewer than 5
@@ -139,7 +141,7 @@ constexpr int kHdrRootHead = 3;     // header word: queue position over the heav
 constexpr int kHdrTaskBad = 9;      // diagnostics: tasks that could not be replayed (must stay 0)
 
 // Claim a slot of the heavy list for `lig` (whole warp; -1: the list is full) and clear its accumulator. `root` = the
-// warp gives the ligand up: round 0 walks its whole tree (else the warp keeps walking and only donates).
+// warp gives the ligand up: a root task walks its whole tree (else the warp keeps walking and only donates).
 __device__ __forceinline__ int heavy_append(unsigned char* workspace, uint32_t* heavy_list, uint32_t* heavy_acc,
                                             uint32_t lig, int lane, bool root) {
   unsigned hi = 0;
@@ -229,7 +231,7 @@ struct KernelArgs {
   const uint32_t* list;  // non-null: the queue runs over this list of ligands (only_status still filters)
   int list_count_word;   // header word holding the list's length
   int list_cap;
-  uint32_t heavy_budget;   // tree nodes after which a ligand is abandoned as PMNET_LIG_HEAVY (0: never)
+  uint32_t heavy_budget;   // tree nodes after which a walker starts giving subtrees away (0: never)
   uint32_t* heavy_list;    // [kHeavyCap] ligand indices (count in header word 1)
   uint32_t* heavy_acc;     // [kHeavyCap][kAccWords]
   uint32_t* task_buf;      // [kTaskCap][kTaskWords] task descriptors
@@ -374,19 +376,19 @@ __global__ void build_edge_table_kernel(const EdgeTableArgs a) {
 
 #include "scoring_fast.cuh"
 
-// TK = task kernel: one round of the task-parallel walk of the heavy ligands (see kHeavyCap).
+// TK = task kernel: the general kernel's code behind the task queue of the heavy ligands (see kHeavyCap).
 template <int W, bool TG, bool TK = false>
 __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_kernel(const KernelArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int CW = 32 * W;  // conformer slots per row
-  constexpr bool DON = TK || W == 1;  // this instantiation can donate subtrees to the task rounds
+  constexpr bool DON = TK || W == 1;  // this instantiation can donate subtrees to the task queue
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
   const PmModel& gm = args.model;
   const int NM = gm.n_nodes, KM = gm.n_clusters;
   if (TK && !(args.task_round == 0 && args.ligands_first)) {
-    // nothing queued for this round (the normal case): return before the model is loaded
+    // nothing queued for this launch (the normal case): return before the model is loaded
     const unsigned int* hdr = (const unsigned int*)args.workspace;
     if (hdr[1] == 0u || (args.task_round != 0 && hdr[kHdrTaskHead] >= min(hdr[kHdrTaskCount], (unsigned)kTaskCap))) return;
   }
@@ -1466,7 +1468,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
     }
     if (heavy) {
       // this warp donated parts of the tree: its own part is folded into the accumulator like a task's, and
-      // pmnet_heavy_finish_kernel writes the ligand's outputs after the last round (W == 1)
+      // pmnet_heavy_finish_kernel writes the ligand's outputs after the last task launch (W == 1)
       atomicMax((int*)task_acc + lane, __float_as_int(best[0]));
       if (lane == 0) {
         atomicAdd(task_acc + kAccNodes, st_nodes);
@@ -1504,7 +1506,7 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
 }
 
 
-// One warp per heavy ligand, after the last task round: score, status and statistics from the accumulator.
+// One warp per heavy ligand, after the last task launch: score, status and statistics from the accumulator.
 struct FinishArgs {
   const unsigned char* workspace;
   const uint32_t* heavy_list;
