@@ -33,12 +33,15 @@ models = {n: PackedModel.from_model(PharmacophoreModel.load(os.path.join(G, f"mo
 models["hot70"] = PackedModel.from_model(
     PharmacophoreModel.create("", (0.0, 0.0, 0.0), synthetic.make_hotspot_infos(seed=21, n_hotspots=70))
 )
+# optional argument: a node budget for the task-parallel walk (PmScoreConfig.heavy_budget; default: the library's)
+BUDGET = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+print(f"heavy_budget = {BUDGET} (0 = default)", flush=True)
 bad = 0
 for name, nconf, n, seed, kw in CASES:
     t0 = time.time()
     batch = LigandBatch.from_typed(synthetic.make_ligands(n, nconf, seed=seed, **kw))
     dm = scoring.DeviceModel(models[name], "cuda:0")
-    out = scoring.score_library(dm, batch, with_stats=True)
+    out = scoring.score_library(dm, batch, config=scoring.ScoreConfig(heavy_budget=BUDGET), with_stats=True)
     ref = orc.score(models[name], batch)
     rel = np.abs(out["scores"] - ref["scores"]) / np.maximum(np.abs(ref["scores"]), 1e-12)
     same_status = np.array_equal(out["status"], ref["status"])
