@@ -183,6 +183,118 @@ __global__ void __launch_bounds__(128) lateral_kernel(const void* __restrict__ x
   }
 }
 
+// ------------------------------------------------------------------ lateral 1x1 conv on the tensor cores (bf16 mode)
+// The two large FPN laterals (64^3 x 33 -> 96 and 32^3 x 96 -> 96, fp32 NCDHW inputs from the image / the backbone) are
+// 13 + 5 GFLOP per 8 pockets: on CUDA cores (lateral_kernel<0>) they ran at ~20 % of the fp32 peak, 1.1 ms of the
+// 8.5 ms forward. Here a 128-voxel tile of x is transposed to bf16 [voxel][k] in shared memory and multiplied by the
+// bf16 weights with mma.sync m16n8k16 (fp32 accumulate); an n8 tile is exactly one 8-channel chunk of the c8 output,
+// so the accumulator fragments are stored (scale / bias / ReLU / + upsampled coarser level) without any shuffle. The
+// kernel is bound by its 0.7 GB of traffic, not by the 72 HMMAs per warp tile. Used when neither input nor output
+// carries a low part: the split-precision mode keeps the fp32 CUDA-core kernel.
+constexpr int kLmVox = 128;  // voxels per tile = 4 warps x 32
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int KT>  // K tiles of 16: C_in <= 16 KT
+__global__ void __launch_bounds__(128, 4) lateral_mma_kernel(const float* __restrict__ x, int cin, const float* __restrict__ wt,
+                                                          const float* __restrict__ scale, const float* __restrict__ bias,
+                                                          int relu, const uint32_t* __restrict__ up,
+                                                          uint32_t* __restrict__ out, int D, int H, int W, int tiles_per_block) {
+  constexpr int KP = 16 * KT + 2;  // row pitch in bf16: KP / 2 odd -> conflict-free transposing stores
+  __shared__ __align__(16) __nv_bfloat16 Wt[96 * KP];     // [n][k]
+  __shared__ __align__(16) __nv_bfloat16 Xs[kLmVox * KP];  // [voxel][k]
+  const int V = D * H * W, Vu = (D / 2) * (H / 2) * (W / 2);
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, c = lane & 3;
+  for (int i = threadIdx.x; i < 96 * 16 * KT; i += blockDim.x) {
+    const int n = i / (16 * KT), k = i % (16 * KT);
+    Wt[n * KP + k] = __float2bfloat16(k < cin ? wt[k * 96 + n] : 0.0f);
+  }
+  const float* xb = x + (size_t)b * cin * V;
+  for (int tile = 0; tile < tiles_per_block; ++tile) {
+    const int v0 = (blockIdx.x * tiles_per_block + tile) * kLmVox;
+    if (v0 >= V) break;
+    __syncthreads();  // Wt written / the previous tile's Xs consumed
+    {
+      const int v = v0 + threadIdx.x;
+      __nv_bfloat162* row = reinterpret_cast<__nv_bfloat162*>(Xs + threadIdx.x * KP);
+#pragma unroll 4
+      for (int k = 0; k < 16 * KT; k += 2) {
+        const float f0 = (k < cin && v < V) ? __ldg(xb + (size_t)k * V + v) : 0.0f;
+        const float f1 = (k + 1 < cin && v < V) ? __ldg(xb + (size_t)(k + 1) * V + v) : 0.0f;
+        row[k >> 1] = __floats2bfloat162_rn(f0, f1);
+      }
+    }
+    __syncthreads();
+    float acc[2][12][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 12; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.0f;
+    const uint32_t* Xw = reinterpret_cast<const uint32_t*>(Xs);
+    const uint32_t* Ww = reinterpret_cast<const uint32_t*>(Wt);
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r = warp * 32 + mt * 16 + g;
+        a[mt][0] = Xw[(r * KP + kt * 16 + 2 * c) >> 1];
+        a[mt][1] = Xw[((r + 8) * KP + kt * 16 + 2 * c) >> 1];
+        a[mt][2] = Xw[(r * KP + kt * 16 + 8 + 2 * c) >> 1];
+        a[mt][3] = Xw[((r + 8) * KP + kt * 16 + 8 + 2 * c) >> 1];
+      }
+#pragma unroll
+      for (int nt = 0; nt < 12; ++nt) {
+        const int n = nt * 8 + g;
+        const uint32_t b0 = Ww[(n * KP + kt * 16 + 2 * c) >> 1];
+        const uint32_t b1 = Ww[(n * KP + kt * 16 + 8 + 2 * c) >> 1];
+        mma_bf16_16816(acc[0][nt], a[0], b0, b1);
+        mma_bf16_16816(acc[1][nt], a[1], b0, b1);
+      }
+    }
+    // epilogue: fragment (row g / g + 8, columns 2c, 2c + 1 of n tile nt) -> channels 8 nt + 2c, + 1 of that voxel
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int v = v0 + warp * 32 + mt * 16 + g + 8 * half;
+        if (v >= V) continue;
+        const int w = v % W, h = (v / W) % H, d = v / (W * H);
+        const int vu = ((d >> 1) * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1);
+#pragma unroll
+        for (int nt = 0; nt < 12; ++nt) {
+          const int ch = nt * 8 + 2 * c;
+          float y0 = acc[mt][nt][2 * half], y1 = acc[mt][nt][2 * half + 1];
+          if (scale) {
+            y0 = fmaf(y0, __ldg(scale + ch), __ldg(bias + ch));
+            y1 = fmaf(y1, __ldg(scale + ch + 1), __ldg(bias + ch + 1));
+          }
+          if (relu) {
+            y0 = fmaxf(y0, 0.0f);
+            y1 = fmaxf(y1, 0.0f);
+          }
+          if (up) {
+            const uint32_t u = __ldg(up + (((size_t)b * 12 + nt) * Vu + vu) * 4 + c);
+            const float2 uf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+            y0 += uf.x;
+            y1 += uf.y;
+          }
+          const __nv_bfloat162 o = __floats2bfloat162_rn(y0, y1);
+          out[(((size_t)b * 12 + nt) * V + v) * 4 + c] = *reinterpret_cast<const uint32_t*>(&o);
+        }
+      }
+  }
+}
+
 // ------------------------------------------------------------------ per-box combine
 // out[j] = act(scale * (S + u_j + [v in P_j] p_j) + bias) + up_j ; thread = (voxel, chunk), loops over boxes.
 // P_j = up to 4 voxel ids per box (-1 padded): the token voxels of the box's group of 4 (mask_head.py:190-194).
@@ -330,6 +442,18 @@ int pmnet_lateral_c96_split(const void* x, const void* x_lo, int32_t x_is_c8, in
       lateral_kernel<1><<<grid, 128, smem, stream>>>(x, c_in, w_t, scale, bias, relu, (const uint4*)up_c8, (uint4*)out_c8,
                                                      D, H, W, (const uint4*)x_lo, (const uint4*)up_lo_c8,
                                                      (uint4*)out_lo_c8);
+  } else if (!out_lo_c8 && !up_lo_c8 && c_in <= 96 && V >= 8192) {
+    // bf16 mode, large level: tensor cores (lateral_mma_kernel); 4 tiles of 128 voxels per block like the kernel below
+    const int tiles = 4;
+    dim3 mgrid((V + kLmVox * tiles - 1) / (kLmVox * tiles), B);
+    const float* xf = (const float*)x;
+    e = cudaSuccess;
+    if (c_in <= 48)
+      lateral_mma_kernel<3><<<mgrid, 128, 0, stream>>>(xf, c_in, w_t, scale, bias, relu, (const uint32_t*)up_c8,
+                                                       (uint32_t*)out_c8, D, H, W, tiles);
+    else
+      lateral_mma_kernel<6><<<mgrid, 128, 0, stream>>>(xf, c_in, w_t, scale, bias, relu, (const uint32_t*)up_c8,
+                                                       (uint32_t*)out_c8, D, H, W, tiles);
   } else {
     e = cudaFuncSetAttribute(lateral_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)

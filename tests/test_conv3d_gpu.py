@@ -76,3 +76,38 @@ def test_fused_head_matches_1x1_conv():
     assert torch.equal(head, head_only)
     assert (head - href).abs().max().item() <= 1e-3 * max(1.0, href.abs().max().item())
     assert y_c8 is not None
+
+
+@pytest.mark.parametrize("cin,res", [(33, 32), (96, 32), (96, 16), (192, 8)])
+def test_fpn_lateral_matches_torch(cin, res):
+    """pmnet_lateral_c96 on an fp32 NCDHW input: relu(bn(conv1x1(x))) + nearest-upsampled coarser level
+    (fpn_decoder.py:100-111). Levels of >= 8192 voxels with C_in <= 96 run on the tensor cores (bf16 operands, fp32
+    accumulation: error ~ 2^-9 of |x| . |w| summed over C_in), the others on the fp32 CUDA-core kernel."""
+    import ctypes as C
+
+    from pharmaconet_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(cin + res)
+    B = 2
+    x = torch.randn((B, cin, res, res, res), generator=g, device="cuda")
+    w = torch.randn((96, cin), generator=g, device="cuda") * cin**-0.5
+    scale = torch.rand(96, generator=g, device="cuda") + 0.5
+    bias = torch.randn(96, generator=g, device="cuda") * 0.1
+    up = torch.randn((B, 96, res // 2, res // 2, res // 2), generator=g, device="cuda").bfloat16()
+    up_c8 = conv.to_c8(up.float())
+    out = torch.empty((B, 12, res, res, res, 8), dtype=torch.bfloat16, device="cuda")
+    w_t = w.t().contiguous()
+    rc = L.pmnet_lateral_c96(
+        x.data_ptr(), 0, cin, w_t.data_ptr(), scale.data_ptr(), bias.data_ptr(), 1, up_c8.data_ptr(), out.data_ptr(),
+        B, res, res, res, C.c_void_p(torch.cuda.current_stream().cuda_stream),
+    )  # fmt: skip
+    _lib.check(rc, "pmnet_lateral_c96")
+    torch.cuda.synchronize()
+    tensor_cores = res**3 >= 8192 and cin <= 96
+    xr, wr = (x.bfloat16().double(), w.bfloat16().double()) if tensor_cores else (x.double(), w.double())
+    ref = torch.relu(torch.einsum("bcdhw,oc->bodhw", xr, wr) * scale.double().view(1, -1, 1, 1, 1) + bias.double().view(1, -1, 1, 1, 1))
+    ref = ref + torch.nn.functional.interpolate(up.double(), scale_factor=2, mode="nearest")
+    got = conv.from_c8(out).double()
+    # the output itself is bf16: half an ulp of the largest value, plus fp32 accumulation noise
+    assert float((got - ref).abs().max()) <= 2.0**-8 * float(ref.abs().max()) + 1e-3
