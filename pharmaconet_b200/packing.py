@@ -14,6 +14,7 @@ The layouts are documented in DESIGN.md and declared for C in include/pmnet_b200
 from __future__ import annotations
 
 import math
+import os
 from collections.abc import Iterable, Sequence
 from dataclasses import dataclass
 
@@ -299,12 +300,42 @@ class LigandBatch:
 
 
 def save_library(path, batch: LigandBatch, names: Sequence[str] | None = None) -> None:
-    """Packed library on disk (.npz): the LigandBatch arrays + optional ligand names (one per ligand)."""
-    extra = {} if names is None else {"names": np.asarray(list(names))}
-    np.savez(path, **batch.arrays(), **extra)
+    """Packed library on disk: the LigandBatch arrays + optional ligand names (one per ligand).
+    `path` ending in .npz -> one file; anything else -> a DIRECTORY with one .npy per array (+ names.txt), which
+    `load_library` memory-maps: a library larger than host memory is then streamed block by block from the page cache
+    / the disk by `Screener.screen_host` (its blocks are slices of these arrays)."""
+    path = os.fspath(path)
+    if path.endswith(".npz"):
+        extra = {} if names is None else {"names": np.asarray(list(names))}
+        np.savez(path, **batch.arrays(), **extra)
+        return
+    os.makedirs(path, exist_ok=True)
+    for k, v in batch.arrays().items():
+        np.save(os.path.join(path, k + ".npy"), np.ascontiguousarray(v))
+    if names is not None:
+        with open(os.path.join(path, "names.txt"), "w") as f:
+            f.write("\n".join(str(n).replace("\n", " ") for n in names))
 
 
-def load_library(path) -> tuple[LigandBatch, list[str]]:
+def is_library_dir(path) -> bool:
+    return os.path.isdir(path) and os.path.isfile(os.path.join(path, "coords.npy"))
+
+
+def load_library(path, mmap: bool = True) -> tuple[LigandBatch, list[str]]:
+    """Load a packed library written by `save_library`. A directory library is memory-mapped (copy-on-write: nothing is
+    read until a block is sliced, nothing is ever written back) unless mmap=False."""
+    path = os.fspath(path)
+    if is_library_dir(path):
+        mode = "c" if mmap else None
+        arrays = {k: np.load(os.path.join(path, k + ".npy"), mmap_mode=mode) for k in LigandBatch.__dataclass_fields__}
+        batch = LigandBatch.from_arrays(arrays)
+        nf = os.path.join(path, "names.txt")
+        if os.path.isfile(nf):
+            with open(nf) as f:
+                names = f.read().split("\n")
+        else:
+            names = [f"ligand_{i}" for i in range(batch.num_ligands)]
+        return batch, names
     z = np.load(path, allow_pickle=False)
     batch = LigandBatch.from_arrays({k: z[k] for k in LigandBatch.__dataclass_fields__})
     names = [str(n) for n in z["names"]] if "names" in z.files else [f"ligand_{i}" for i in range(batch.num_ligands)]

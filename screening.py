@@ -24,7 +24,7 @@ def parse_args():
     p = argparse.ArgumentParser("scoring", formatter_class=argparse.ArgumentDefaultsHelpFormatter)
     cfg = p.add_argument_group("config")
     cfg.add_argument("-p", "--pharmacophore_model", type=str, required=True, help="path of pharmacophore model (.pm | .json)")
-    cfg.add_argument("-d", "--library_dir", type=str, required=True, help="molecular library directory, or a packed .npz")
+    cfg.add_argument("-d", "--library_dir", type=str, required=True, help="molecular library directory, a packed .npz, or a packed (memory-mapped) library directory")
     cfg.add_argument("-o", "--out", type=str, required=True, help="result file path")
     cfg.add_argument("--cpus", type=int, default=1, help="number of cpus (ligand typing workers)")
     cfg.add_argument("--num_conformers", type=int, default=None, help="use only the first N conformers of each file")
@@ -47,11 +47,11 @@ def _type_file(job):
 
 
 def load_library(args):
-    from pharmaconet_b200.packing import LigandBatch, load_library
+    from pharmaconet_b200.packing import LigandBatch, is_library_dir, load_library
 
     src = Path(args.library_dir)
-    if src.is_file() and src.suffix == ".npz":
-        return load_library(src)
+    if (src.is_file() and src.suffix == ".npz") or is_library_dir(src):
+        return load_library(src)  # (a packed directory is memory-mapped: blocks are read as they are streamed)
     files = sorted(src.rglob("*.sdf")) + sorted(src.rglob("*.mol2"))
     print(f"find {len(files)} molecules")
     jobs = [(str(f), args.num_conformers) for f in files]
@@ -87,7 +87,9 @@ def main():
     )  # fmt: skip
     library, names = load_library(args)
     scr = Screener(model, weights=weights, k=min(1000, max(1, library.num_ligands)))
-    if library.coords.nbytes >= (64 << 20):
+    from pharmaconet_b200.packing import is_library_dir
+
+    if library.coords.nbytes >= (64 << 20) and not is_library_dir(args.library_dir):
         from pharmaconet_b200.screening import pin_library
 
         library = pin_library(library)  # page-locked: block copies overlap the scoring kernel

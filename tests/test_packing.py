@@ -42,3 +42,32 @@ def test_coord_layout_alignment():
     assert np.all(b.coord_off % 4 == 0)
     stride = (b.n_conf + 3) // 4 * 4
     assert np.array_equal(np.diff(b.coord_off), np.diff(b.lig_node_off) * 3 * stride)
+
+
+def test_library_directory_is_memory_mapped_and_equal(tmp_path):
+    """save_library to a directory (one .npy per array) / load_library memory-maps it: the arrays are views of the
+    files (no copy at load time), blocks sliced from them equal the in-memory library, names survive."""
+    from pharmaconet_b200 import synthetic
+    from pharmaconet_b200.packing import is_library_dir, load_library, save_library
+
+    batch = LigandBatch.from_typed(synthetic.make_ligands(50, 4, seed=5))
+    names = [f"mol_{i}" for i in range(50)]
+    d = tmp_path / "lib_dir"
+    save_library(d, batch, names)
+    assert is_library_dir(d) and not is_library_dir(tmp_path)
+    lib, got_names = load_library(d)
+    assert got_names == names
+    for k, v in batch.arrays().items():
+        w = lib.arrays()[k]
+        assert np.array_equal(v, w) and v.dtype == w.dtype, k
+    base = lib.coords
+    while getattr(base, "base", None) is not None and not isinstance(base, np.memmap):
+        base = base.base
+    assert isinstance(base, np.memmap)  # still backed by the file
+    sub = lib.select(np.arange(10, 20))
+    ref = batch.select(np.arange(10, 20))
+    assert np.array_equal(sub.coords, ref.coords) and np.array_equal(sub.node_type_mask, ref.node_type_mask)
+    # the single-file form still round-trips
+    save_library(tmp_path / "lib.npz", batch, names)
+    lib2, names2 = load_library(tmp_path / "lib.npz")
+    assert names2 == names and np.array_equal(lib2.coords, batch.coords)

@@ -212,6 +212,39 @@ def test_screening_cli_on_packed_library(tmp_path):
     assert max(abs(got[n] - ref[n]) / max(abs(ref[n]), 1e-12) for n in names) <= REL_TOL
 
 
+def test_screening_over_a_memory_mapped_library_directory(tmp_path):
+    """A library saved as a directory of .npy files is memory-mapped by load_library: Screener.screen_host streams its
+    blocks straight from the mapped arrays (pageable copies), and the CLI accepts the directory - same scores."""
+    import os
+    import subprocess
+    import sys
+
+    from golden_util import GOLDEN
+
+    from pharmaconet_b200 import screening
+    from pharmaconet_b200.packing import load_library, save_library
+
+    c = load_case("syn0_c8")
+    names = [f"lig_{i:04d}.sdf" for i in range(c["batch"].num_ligands)]
+    save_library(tmp_path / "lib_dir", c["batch"], names)
+    lib, got_names = load_library(tmp_path / "lib_dir")
+    assert got_names == names
+    whole = _run(c["model"], c["batch"], None)["scores"]
+    res = screening.Screener(c["model"], "cuda:0", k=16, block_ligands=64).screen_host(lib)
+    assert np.array_equal(res.scores, whole)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "out.csv"
+    subprocess.run(
+        [sys.executable, os.path.join(root, "screening.py"), "-p", os.path.join(GOLDEN, "model_syn0.pm"),
+         "-d", str(tmp_path / "lib_dir"), "-o", str(out)],
+        check=True, cwd=root, timeout=300,
+    )  # fmt: skip
+    lines = out.read_text().splitlines()
+    got = {ln.split(",")[0]: float(ln.split(",")[1]) for ln in lines[1:]}
+    ref = dict(zip(names, c["ref"]))
+    assert max(abs(got[n] - ref[n]) / max(abs(ref[n]), 1e-12) for n in names) <= REL_TOL
+
+
 def test_more_than_32_conformers_mixed_batch():
     # 2 and 4 conformers per lane, mixed with short ligands in the same launch; per-conformer maxima too
     c = load_case("syn0_c100")

@@ -9,6 +9,8 @@ One ligand per file, every record a conformer (the reference's convention, src/p
 `.sdf` files are typed with OpenBabel when it is importable (the reference's perception), else with the built-in
 approximate reader; `.mol2` / `.pdb` need OpenBabel. Files that fail to parse are reported and skipped.
 The file holds the `LigandBatch` arrays (layouts: include/pmnet_b200.h, struct PmLigandBatch) plus `names`.
+An output path that does not end in `.npz` becomes a DIRECTORY with one `.npy` per array: `screening.py -d that_dir`
+memory-maps it, so a library larger than host memory is streamed from disk block by block.
 """
 
 from __future__ import annotations
