@@ -212,9 +212,9 @@ __global__ void __launch_bounds__(128, 4) lateral_mma_kernel(const float* __rest
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, c = lane & 3;
-  for (int i = threadIdx.x; i < 96 * 16 * KT; i += blockDim.x) {
-    const int n = i / (16 * KT), k = i % (16 * KT);
-    Wt[n * KP + k] = __float2bfloat16(k < cin ? wt[k * 96 + n] : 0.0f);
+  for (int i = threadIdx.x; i < 96 * 16 * KT; i += blockDim.x) {  // (coalesced reads of wt[k][n])
+    const int k = i / 96, n = i % 96;
+    Wt[n * KP + k] = __float2bfloat16(k < cin ? wt[i] : 0.0f);
   }
   const float* xb = x + (size_t)b * cin * V;
   for (int tile = 0; tile < tiles_per_block; ++tile) {
@@ -443,8 +443,8 @@ int pmnet_lateral_c96_split(const void* x, const void* x_lo, int32_t x_is_c8, in
                                                      D, H, W, (const uint4*)x_lo, (const uint4*)up_lo_c8,
                                                      (uint4*)out_lo_c8);
   } else if (!out_lo_c8 && !up_lo_c8 && c_in <= 96 && V >= 8192) {
-    // bf16 mode, large level: tensor cores (lateral_mma_kernel); 4 tiles of 128 voxels per block like the kernel below
-    const int tiles = 4;
+    // bf16 mode, large level: tensor cores (lateral_mma_kernel)
+    const int tiles = V >= (1 << 18) ? 2 : 1;  // enough blocks for several waves at every level
     dim3 mgrid((V + kLmVox * tiles - 1) / (kLmVox * tiles), B);
     const float* xf = (const float*)x;
     e = cudaSuccess;
