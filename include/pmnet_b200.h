@@ -126,8 +126,8 @@ typedef struct PmScoreConfig {
                                 of the library and no compaction */
   int32_t heavy_budget;      /* tree nodes after which a ligand's tree is shared out: the warp walking it (and every
                                 warp that takes a piece) gives unvisited subtrees away to a task queue served inside
-                                the same call; 0: default 65536, < 0: never. Only with max_conformers <= 32 and
-                                rescore_status == 0. Scores, per-conformer scores and tree statistics do not depend
+                                the same call; 0: default 65536, < 0: never. Not on status-restricted re-runs
+                                (rescore_status != 0). Scores, per-conformer scores and tree statistics do not depend
                                 on it */
   int32_t reserved[2];
 } PmScoreConfig;

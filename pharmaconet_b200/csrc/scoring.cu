@@ -125,8 +125,8 @@ constexpr size_t kHeaderBytes = 256;
 // atomicMax on non-negative floats: exact, order independent) and its node / leaf counts (atomicAdd) into the ligand's
 // accumulator, and pmnet_heavy_finish_kernel writes score, status and statistics - identical to the un-split walk.
 constexpr int kHeavyCap = 65536;   // heavy ligands split per call (more are walked to the end where they are)
-constexpr int kAccWords = 40;      // per heavy ligand: best[32], nodes, leaves, rows, pairs, needs a root task, -
-constexpr int kAccNodes = 32, kAccLeaves = 33, kAccRows = 34, kAccPairs = 35, kAccRoot = 36;
+constexpr int kAccWords = 136;     // per heavy ligand: best[128], nodes, leaves, rows, pairs, needs a root task, -
+constexpr int kAccNodes = 128, kAccLeaves = 129, kAccRows = 130, kAccPairs = 131, kAccRoot = 132;
 constexpr int kTaskWords = 32;     // [0] heavy slot, [1] depth j, [4 + i] entry chosen at level i <= j (~0: the None child)
 constexpr int kTaskCap = 1 << 18;  // tasks per call (a full queue: the walker keeps its candidates)
 constexpr int kTaskRounds = 3;
@@ -150,8 +150,7 @@ __device__ __forceinline__ int heavy_append(unsigned char* workspace, uint32_t* 
   if (hi >= (unsigned)kHeavyCap) return -1;
   if (lane == 0) heavy_list[hi] = lig;
   uint32_t* acc = heavy_acc + (size_t)hi * kAccWords;
-  acc[lane] = 0u;
-  if (lane < kAccWords - 32) acc[32 + lane] = (lane == kAccRoot - 32 && root) ? 1u : 0u;
+  for (int i = lane; i < kAccWords; i += 32) acc[i] = (i == kAccRoot && root) ? 1u : 0u;
   return (int)hi;
 }
 
@@ -381,7 +380,7 @@ template <int W, bool TG, bool TK = false>
 __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_kernel(const KernelArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int CW = 32 * W;  // conformer slots per row
-  constexpr bool DON = TK || W == 1;  // this instantiation can donate subtrees to the task queue
+  constexpr bool DON = true;  // (every instantiation can donate subtrees to the task queue)
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
@@ -1448,12 +1447,13 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
       (void)lane_on;
     }
     if (TK && is_task) {
-      // fold the task into the ligand's accumulator (pmnet_heavy_finish_kernel); W == 1
+      // fold the task into the ligand's accumulator (pmnet_heavy_finish_kernel)
       if (status != PMNET_LIG_OK || task_bad) {
         if (lane == 0) atomicAdd((unsigned int*)args.workspace + kHdrTaskBad, 1u);
       } else {
         // scores are >= 0 (best starts at 0): their bit patterns order like integers
-        atomicMax((int*)task_acc + lane, __float_as_int(best[0]));
+#pragma unroll
+        for (int w = 0; w < W; ++w) atomicMax((int*)task_acc + 32 * w + lane, __float_as_int(best[w]));
         if (lane == 0) {
           atomicAdd(task_acc + kAccNodes, st_nodes);
           atomicAdd(task_acc + kAccLeaves, st_leaves);
@@ -1468,8 +1468,9 @@ __global__ void __launch_bounds__(block_threads(W), min_blocks(W)) pmnet_score_k
     }
     if (heavy) {
       // this warp donated parts of the tree: its own part is folded into the accumulator like a task's, and
-      // pmnet_heavy_finish_kernel writes the ligand's outputs after the last task launch (W == 1)
-      atomicMax((int*)task_acc + lane, __float_as_int(best[0]));
+      // pmnet_heavy_finish_kernel writes the ligand's outputs after the last task launch
+#pragma unroll
+      for (int w = 0; w < W; ++w) atomicMax((int*)task_acc + 32 * w + lane, __float_as_int(best[w]));
       if (lane == 0) {
         atomicAdd(task_acc + kAccNodes, st_nodes);
         atomicAdd(task_acc + kAccLeaves, st_leaves);
@@ -1528,9 +1529,14 @@ __global__ void __launch_bounds__(128) pmnet_heavy_finish_kernel(const FinishArg
   for (unsigned h = warp; h < nh; h += nwarps) {
     const uint32_t lig = args.heavy_list[h];
     const uint32_t* const acc = args.heavy_acc + (size_t)h * kAccWords;
-    const float best = __int_as_float((int)acc[lane]);
     const int C = args.n_conf[lig];
-    double s = lane < C ? (double)best : 0.0;  // mean over conformers (graph_match.py:109), like the walkers
+    const int nw = args.conf_stride / 32;  // conformer words per lane (1, 2 or 4)
+    float best[4];
+    double s = 0.0;  // mean over conformers (graph_match.py:109): the same sum, in the same order, as the walkers'
+    for (int w = 0; w < nw; ++w) {
+      best[w] = __int_as_float((int)acc[32 * w + lane]);
+      s += (lane + 32 * w < C) ? (double)best[w] : 0.0;
+    }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
     if (lane == 0) {
       args.out_scores[lig] = (float)(s / (double)C);
@@ -1543,7 +1549,8 @@ __global__ void __launch_bounds__(128) pmnet_heavy_finish_kernel(const FinishArg
         o[3] = acc[kAccPairs];
       }
     }
-    if (args.out_conf) args.out_conf[(size_t)lig * args.conf_stride + lane] = best;
+    if (args.out_conf)
+      for (int w = 0; w < nw; ++w) args.out_conf[(size_t)lig * args.conf_stride + 32 * w + lane] = best[w];
   }
 }
 
@@ -1592,11 +1599,10 @@ size_t fast_workspace_bytes() {
   return kHeaderBytes + (size_t)sm_count_cached() * fastk::kCtasPerSm * fastk::kWarps * fastk::G_BYTES;
 }
 
-// Node budget of the task-parallel walk for this configuration (0: off). One conformer word only (the task records
-// hold 32 per-conformer scores), and not on a status-restricted re-run.
+// Node budget of the task-parallel walk for this configuration (0: off): not on a status-restricted re-run.
 uint32_t heavy_budget_of(const PmScoreConfig* in) {
   if (!in) return kDefaultHeavyBudget;
-  if (in->heavy_budget < 0 || in->rescore_status != 0 || in->max_conformers > 32) return 0u;
+  if (in->heavy_budget < 0 || in->rescore_status != 0) return 0u;
   return in->heavy_budget > 0 ? (uint32_t)in->heavy_budget : kDefaultHeavyBudget;
 }
 
@@ -1696,7 +1702,7 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
   const bool fast = W == 1 && !tg && use_fast_kernel(cfg, model->n_nodes, model->n_clusters, n_cluster_nodes);
   a.only_status = (cfg && cfg->rescore_status != 0) ? cfg->rescore_status : -1;
   a.counter_word = 0;
-  a.heavy_budget = W == 1 ? heavy_budget_of(cfg) : 0u;
+  a.heavy_budget = heavy_budget_of(cfg);
   a.heavy_list = (uint32_t*)((unsigned char*)workspace + scratch_bytes(model->n_nodes, model->n_clusters, cfg));
   a.heavy_acc = a.heavy_list + kHeavyCap;
   a.task_buf = a.heavy_acc + (size_t)kHeavyCap * kAccWords;
@@ -1782,7 +1788,10 @@ int pmnet_score_batch(const PmModel* model, const PmLigandBatch* batch, const fl
     // ligand queue like the general kernel would, then the ligands the specialised kernel gave up and the task queue
     // (its walkers donate into the queue it is consuming); the others return at once unless something is left over.
     // Then the kernel that turns the accumulators of the heavy ligands into scores
-    const void* tfn = tg ? (const void*)pmnet_score_kernel<1, true, true> : (const void*)pmnet_score_kernel<1, false, true>;
+    const void* tfn;
+    if (W == 1) tfn = tg ? (const void*)pmnet_score_kernel<1, true, true> : (const void*)pmnet_score_kernel<1, false, true>;
+    else if (W == 2) tfn = tg ? (const void*)pmnet_score_kernel<2, true, true> : (const void*)pmnet_score_kernel<2, false, true>;
+    else tfn = tg ? (const void*)pmnet_score_kernel<4, true, true> : (const void*)pmnet_score_kernel<4, false, true>;
     e = cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_err(cudaGetErrorString(e));

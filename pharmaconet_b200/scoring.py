@@ -109,13 +109,13 @@ class ScoreConfig:
 def launches_per_call(config: "ScoreConfig | None" = None, max_conformers: int = 32) -> int:
     """Kernels one pmnet_score_batch call enqueues (csrc/scoring.cu): the specialised kernel (default launch shape and
     <= 32 conformers only; models whose tables do not fit in shared memory skip it), then either the general kernel
-    (heavy_budget < 0, more than 32 conformers, or a status-restricted re-run) or three launches of the task kernel -
+    (heavy_budget < 0 or a status-restricted re-run) or three launches of the task kernel -
     the first serves the ligand queue like the general kernel and then the tasks its walkers donate, the others return
     at once when nothing is left - plus the kernel that finishes the heavy ligands."""
     cfg = config or ScoreConfig()
     custom = cfg.warps_per_block > 0 or cfg.blocks > 0 or cfg.scratch_rows > 0 or cfg.rescore_status != 0
     n = int(not custom and max_conformers <= 32)
-    heavy = cfg.heavy_budget >= 0 and cfg.rescore_status == 0 and max_conformers <= 32
+    heavy = cfg.heavy_budget >= 0 and cfg.rescore_status == 0
     return n + (4 if heavy else 1)
 
 

@@ -529,6 +529,21 @@ def test_task_parallel_walk_is_identical_to_single_warp_walk(name, general_only)
         assert np.array_equal(split["stats"][ok, 1].astype(np.uint32), o["stats"][ok, 1].astype(np.uint32))
 
 
+@pytest.mark.parametrize("nconf", [40, 100])
+def test_task_parallel_walk_with_more_than_32_conformers(nconf):
+    """2 or 4 conformers per lane: the accumulator of a heavy ligand holds up to 128 per-conformer maxima."""
+    c = load_case("syn0_c32")
+    batch = LigandBatch.from_typed(synthetic.make_ligands(600, nconf, seed=431) + synthetic.make_ligands(200, 7, seed=432))
+    base = _score_with_budget(c["model"], batch, -1)
+    split = _score_with_budget(c["model"], batch, 40)
+    assert split["n_heavy"] > 100 and split["n_tasks"] > 0 and split["n_bad"] == 0
+    for k in ("status", "scores", "conf", "stats"):
+        assert np.array_equal(split[k], base[k]), k
+    o = orc.score(c["model"], batch, None)
+    assert rel_err(split["scores"], o["scores"]).max() <= REL_TOL
+    assert np.array_equal(split["stats"][:, 0].astype(np.uint32), o["stats"][:, 0].astype(np.uint32))
+
+
 def test_task_parallel_walk_full_queues():
     """A budget of 8 nodes on 6500 ligands: nearly every ligand goes to the task kernel and is cut into many tasks
     (paths through None children included), taken by idle warps of the same launch as they appear."""
