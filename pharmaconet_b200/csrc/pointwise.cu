@@ -200,14 +200,16 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int KT>  // K tiles of 16: C_in <= 16 KT
+// IN_C8: x is a bf16 c8 activation (C_in = 16 KT exactly): the A fragments are read straight from global memory - 8
+// consecutive voxels of one chunk are 128 contiguous bytes, 4 lanes per voxel - and nothing is staged.
+template <int KT, bool IN_C8 = false>  // K tiles of 16: C_in <= 16 KT
 __global__ void __launch_bounds__(128, 4) lateral_mma_kernel(const float* __restrict__ x, int cin, const float* __restrict__ wt,
                                                           const float* __restrict__ scale, const float* __restrict__ bias,
                                                           int relu, const uint32_t* __restrict__ up,
                                                           uint32_t* __restrict__ out, int D, int H, int W, int tiles_per_block) {
   constexpr int KP = 16 * KT + 2;  // row pitch in bf16: KP / 2 odd -> conflict-free transposing stores
   __shared__ __align__(16) __nv_bfloat16 Wt[96 * KP];     // [n][k]
-  __shared__ __align__(16) __nv_bfloat16 Xs[kLmVox * KP];  // [voxel][k]
+  __shared__ __align__(16) __nv_bfloat16 Xs[IN_C8 ? 8 : kLmVox * KP];  // [voxel][k] (fp32 NCDHW input only)
   const int V = D * H * W, Vu = (D / 2) * (H / 2) * (W / 2);
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(128, 4) lateral_mma_kernel(const float* __rest
     const int v0 = (blockIdx.x * tiles_per_block + tile) * kLmVox;
     if (v0 >= V) break;
     __syncthreads();  // Wt written / the previous tile's Xs consumed
-    {
+    if (!IN_C8) {
       const int v = v0 + threadIdx.x;
       __nv_bfloat162* row = reinterpret_cast<__nv_bfloat162*>(Xs + threadIdx.x * KP);
 #pragma unroll 4
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(128, 4) lateral_mma_kernel(const float* __rest
         row[k >> 1] = __floats2bfloat162_rn(f0, f1);
       }
     }
-    __syncthreads();
+    if (!IN_C8) __syncthreads();
     float acc[2][12][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -247,6 +249,15 @@ __global__ void __launch_bounds__(128, 4) lateral_mma_kernel(const float* __rest
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const int r = warp * 32 + mt * 16 + g;
+        if (IN_C8) {
+          const uint32_t* x32 = reinterpret_cast<const uint32_t*>(x) + ((size_t)b * (2 * KT) + 2 * kt) * V * 4;
+          const int va = v0 + r, vb = va + 8;
+          a[mt][0] = va < V ? __ldg(x32 + (size_t)va * 4 + c) : 0u;
+          a[mt][1] = vb < V ? __ldg(x32 + (size_t)vb * 4 + c) : 0u;
+          a[mt][2] = va < V ? __ldg(x32 + ((size_t)V + va) * 4 + c) : 0u;
+          a[mt][3] = vb < V ? __ldg(x32 + ((size_t)V + vb) * 4 + c) : 0u;
+          continue;
+        }
         a[mt][0] = Xw[(r * KP + kt * 16 + 2 * c) >> 1];
         a[mt][1] = Xw[((r + 8) * KP + kt * 16 + 2 * c) >> 1];
         a[mt][2] = Xw[(r * KP + kt * 16 + 8 + 2 * c) >> 1];
@@ -436,7 +447,14 @@ int pmnet_lateral_c96_split(const void* x, const void* x_lo, int32_t x_is_c8, in
   const int V = D * H * W;
   dim3 grid((V + kLatVox * kLatTiles - 1) / (kLatVox * kLatTiles), B);
   cudaError_t e;
-  if (x_is_c8) {
+  if (x_is_c8 && !x_lo && !out_lo_c8 && !up_lo_c8 && c_in == 96 && V >= 8192) {
+    // bf16 mode, c8 input (the mask head's shared laterals): tensor cores, fragments straight from global memory
+    const int tiles = V >= (1 << 18) ? 2 : 1;
+    dim3 mgrid((V + kLmVox * tiles - 1) / (kLmVox * tiles), B);
+    e = cudaSuccess;
+    lateral_mma_kernel<6, true><<<mgrid, 128, 0, stream>>>((const float*)x, c_in, w_t, scale, bias, relu,
+                                                           (const uint32_t*)up_c8, (uint32_t*)out_c8, D, H, W, tiles);
+  } else if (x_is_c8) {
     e = cudaFuncSetAttribute(lateral_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       lateral_kernel<1><<<grid, 128, smem, stream>>>(x, c_in, w_t, scale, bias, relu, (const uint4*)up_c8, (uint4*)out_c8,

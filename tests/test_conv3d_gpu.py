@@ -111,3 +111,31 @@ def test_fpn_lateral_matches_torch(cin, res):
     got = conv.from_c8(out).double()
     # the output itself is bf16: half an ulp of the largest value, plus fp32 accumulation noise
     assert float((got - ref).abs().max()) <= 2.0**-8 * float(ref.abs().max()) + 1e-3
+
+
+@pytest.mark.parametrize("res", [16, 32])
+def test_lateral_on_c8_input_matches_torch(res):
+    """The mask head's shared laterals: 1x1 conv of a bf16 c8 activation without affine / ReLU / upsample
+    (mask_head.py:170-196 folded, see pmnet_box_combine_c96). >= 8192 voxels: mma.sync with fragments read straight
+    from the c8 tensor; below: the CUDA-core kernel. Same bound either way: the operands are bf16 already."""
+    import ctypes as C
+
+    from pharmaconet_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator(device="cuda").manual_seed(res)
+    B = 2
+    x = torch.randn((B, 96, res, res, res), generator=g, device="cuda").bfloat16()
+    w = (torch.randn((96, 96), generator=g, device="cuda") * 96**-0.5).bfloat16().float()
+    x_c8 = conv.to_c8(x.float())
+    out = torch.empty((B, 12, res, res, res, 8), dtype=torch.bfloat16, device="cuda")
+    w_t = w.t().contiguous()
+    rc = L.pmnet_lateral_c96(
+        x_c8.data_ptr(), 1, 96, w_t.data_ptr(), None, None, 0, None, out.data_ptr(), B, res, res, res,
+        C.c_void_p(torch.cuda.current_stream().cuda_stream),
+    )  # fmt: skip
+    _lib.check(rc, "pmnet_lateral_c96")
+    torch.cuda.synchronize()
+    ref = torch.einsum("bcdhw,oc->bodhw", x.double(), w.double())
+    got = conv.from_c8(out).double()
+    assert float((got - ref).abs().max()) <= 2.0**-8 * float(ref.abs().max()) + 1e-3
